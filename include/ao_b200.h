@@ -1,0 +1,146 @@
+/*
+ * ao_b200.h — C ABI of the B200-native quantized-linear engine (libao_b200.so).
+ *
+ * This is the drop-in boundary for the quantized nn.Linear forward of pytorch/ao
+ * (torchao 0.19).  Every entry point replaces one kernel-level call the reference
+ * makes from its tensor-subclass linear handlers; the reference file:line each one
+ * stands in for is cited beside it.  Signatures are plain device pointers, sizes
+ * and a CUDA stream: no torch types.  The torch.library registration that binds
+ * these as torch.ops.ao_b200.* lives in ao_b200/csrc/torch_binding.cpp.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - matrices are row-major; a linear is Y[M,N] = X[M,K] * W[N,K]^T (+ bias[N]);
+ *   - bf16 values are passed as uint16_t bit patterns;
+ *   - return value: 0 on success, negative AO_ERR_* otherwise, with a message
+ *     retrievable from ao_b200_last_error() (thread-local);
+ *   - kernels never synchronise the device and are CUDA-graph capturable
+ *     (tensor maps are built on the host and passed by value);
+ *   - `workspace` is caller-owned scratch for split-K partials + semaphores; it
+ *     must be zero-initialised once (kernels restore the semaphores to zero) and
+ *     must not be shared by linears running concurrently on different streams.
+ */
+#ifndef AO_B200_H_
+#define AO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AO_OK 0
+#define AO_ERR_INVALID_ARG (-1)
+#define AO_ERR_CUDA (-2)
+#define AO_ERR_UNSUPPORTED (-3)
+#define AO_ERR_WORKSPACE (-4)
+
+/* library / device ---------------------------------------------------------- */
+int ao_b200_version(void);
+const char* ao_b200_last_error(void);
+/* 1 when the current device is compute capability 10.x (sm_100a kernels can run). */
+int ao_b200_device_ok(void);
+/* bytes of workspace any linear below may need for (M, N) outputs. */
+size_t ao_b200_workspace_bytes(int M, int N);
+/* number of kernels this library has launched since load (bench.py "gpu_launches"). */
+uint64_t ao_b200_launch_count(void);
+
+/* int4 weight-only, tile_packed_to_4d ---------------------------------------- */
+/* Replaces aten._convert_weight_to_int4pack(uint8[N,K/2], inner_k_tiles)
+ * (reference call: quantize_/workflows/int4/int4_tile_packed_to_4d_tensor.py:198-204).
+ * in : q_u8[N][K/2], byte = q[n,2j]<<4 | q[n,2j+1];  N%8==0, K%(inner_k_tiles*16)==0
+ * out: int32 [N/8][K/(inner_k_tiles*16)][32][inner_k_tiles/2]                     */
+int ao_int4_pack_tile4d(const uint8_t* q_u8, int32_t* qdata, int N, int K,
+                        int inner_k_tiles, void* stream);
+/* Inverse of the above: qdata -> q_u8[N][K/2] (used by dequantize() and tests). */
+int ao_int4_unpack_tile4d(const int32_t* qdata, uint8_t* q_u8, int N, int K,
+                          int inner_k_tiles, void* stream);
+/* Dequantise to bf16 W^[N][K] = bf16((q-8)*s+z) (the oracle's definition of the weight). */
+int ao_int4_dequant_tile4d(const int32_t* qdata, const uint16_t* scale_and_zero,
+                           uint16_t* w_bf16, int N, int K, int group_size, void* stream);
+/* Replaces aten._weight_int4pack_mm(x, qdata, group_size, scale_and_zero) plus the
+ * bias add / slice the handler does around it
+ * (int4_tile_packed_to_4d_tensor.py:243-299, hot call at :287).
+ * x bf16 [M,K]; qdata int32 [N/8][K/128][32][4]; scale_and_zero bf16 [K/g][N][2];
+ * bias bf16 [N_out] or NULL; y bf16 [M, N_out] with N_out <= N (row stride N_out).
+ * K%1024==0 (the format pads K to 1024), N%8==0, g in {32,64,128,256}.
+ * impl: 0 = auto, 1 = tcgen05 pipeline, 2 = CUDA-core reference-grade kernel.      */
+int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qdata,
+                              const uint16_t* scale_and_zero, int group_size, int N,
+                              const uint16_t* bias, uint16_t* y, int N_out,
+                              void* workspace, size_t workspace_bytes, int impl,
+                              void* stream);
+
+/* int8 dynamic activation x int8 weight --------------------------------------- */
+/* Per-token symmetric int8 quantisation of activations: replaces
+ * Int8Tensor.from_hp(x, PerRow()) on the hot path (int8_tensor.py:176-248 via
+ * quantize_tensor_kwargs.py:36-71).  x bf16 [M,K] -> q int8 [M,K], scale f32 [M].  */
+int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t* q, float* scale,
+                             void* stream);
+/* Replaces _int_scaled_matmul + the epilogue (int8/kernels.py:114-144,
+ * int8_tensor.py:305-359): y = bf16(bf16(acc_i32 * x_scale[m]) * w_scale[n] + bias[n]).
+ * xq int8 [M,K], wq int8 [N,K] (K-major, i.e. the stored qdata), scales f32.         */
+int ao_int8_dyn_linear(const int8_t* xq, const float* x_scale, int M, int K,
+                       const int8_t* wq, const float* w_scale, int N,
+                       const uint16_t* bias, uint16_t* y, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* int32 accumulator only (aten._int_mm equivalent; int8/kernels.py:18-76). */
+int ao_int8_mm_i32(const int8_t* xq, int M, int K, const int8_t* wq, int N, int32_t* acc,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* fp8 e4m3 rowwise -------------------------------------------------------------- */
+/* Replaces _choose_scale_float8 + _quantize_affine_float8 for PerRow activations
+ * (quant_primitives.py:2172-2287, float8_tensor.py:235-242).
+ * x bf16 [M,K] -> q e4m3 [M,K] (bytes), scale f32 [M] = f32(bf16(amax/448)).          */
+int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t* q, float* scale,
+                            void* stream);
+/* Replaces torch._scaled_mm(a, b, scale_a, scale_b, bias, out_dtype=bf16)
+ * (float8/inference.py:86-123 <- float8_tensor.py:449-457).
+ * y = bf16( (Xq Wq^T)[m,n] * x_scale[m] * w_scale[n] + bias[n] ), f32 accumulate.     */
+int ao_fp8_rowwise_linear(const uint8_t* xq, const float* x_scale, int M, int K,
+                          const uint8_t* wq, const float* w_scale, int N,
+                          const uint16_t* bias, uint16_t* y, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* mxfp8 (e4m3 data, e8m0 block-32 scales) --------------------------------------- */
+/* Replaces MXTensor.to_mx(x, e4m3, 32, RCEIL, is_swizzled_scales) for activations
+ * (mx_tensor.py:228-409, :161-225).  x bf16 [M,K] -> q e4m3 [M,K], scales e8m0 bytes;
+ * swizzled=1 writes the 128x4 -> 32x16 blocked layout (mx_formats/utils.py:31-70),
+ * size 32*ceil(M/128) x 16*ceil(K/128); swizzled=0 writes plain [M][K/32].            */
+int ao_mxfp8_quantize(const uint16_t* x, int M, int K, uint8_t* q, uint8_t* scale_e8m0,
+                      int swizzled, void* stream);
+/* Replaces torch._scaled_mm(e4m3, e4m3, e8m0 blocked, e8m0 blocked, bias, bf16)
+ * (mx_tensor.py:803-810).  Both scale tensors are in the blocked layout.              */
+int ao_mxfp8_linear(const uint8_t* xq, const uint8_t* x_scale_blocked, int M, int K,
+                    const uint8_t* wq, const uint8_t* w_scale_blocked, int N,
+                    const uint16_t* bias, uint16_t* y, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* nvfp4 (e2m1 data, e4m3 block-16 scales, f32 per-tensor scale) ------------------ */
+/* Replaces nvfp4_quantize + to_blocked for activations (nvfp4_tensor.py:772-854).
+ * x bf16 [M,K] -> q uint8 [M,K/2] (even k in the LOW nibble), scales e4m3 bytes.
+ * per_tensor_scale: device f32 scalar or NULL (single-level scaling).                 */
+int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* per_tensor_scale,
+                      uint8_t* q, uint8_t* scale_e4m3, int swizzled, void* stream);
+/* Replaces torch._scaled_mm(fp4x2, fp4x2, e4m3 blocked scales) * (a_pts*b_pts) + bias
+ * (nvfp4_tensor.py:487-578).  a_pts / b_pts: device f32 scalars or NULL (=1).          */
+int ao_nvfp4_linear(const uint8_t* xq, const uint8_t* x_scale_blocked, const float* a_pts,
+                    int M, int K, const uint8_t* wq, const uint8_t* w_scale_blocked,
+                    const float* b_pts, int N, const uint16_t* bias, uint16_t* y,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* nvfp4 weight-only / nvfp4-weight x fp8-rowwise activation (BASELINE config 5):
+ * y = bf16( sum_k A^[m,k] * dequant(W)[n,k] * x_scale[m] + bias ), where A^ is bf16
+ * (act_fp8 == 0, x is bf16, x_scale ignored) or e4m3 (act_fp8 == 1).
+ * Semantics = F.linear(x_dq, NVFP4Tensor.dequantize()) (nvfp4_tensor.py:199-231,
+ * inference_workflow.py:356-400).                                                     */
+int ao_nvfp4_weight_linear(const void* x, const float* x_scale, int act_fp8, int M, int K,
+                           const uint8_t* wq, const uint8_t* w_scale_blocked,
+                           const float* b_pts, int N, const uint16_t* bias, uint16_t* y,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AO_B200_H_ */
