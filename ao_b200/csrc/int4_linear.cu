@@ -23,6 +23,7 @@
 //   bits [16+4e, ..) = q[n, k0 + 8e + 1]
 // so one row's 128 k of a k-tile are the 64 contiguous bytes of lanes 4*(n%8)..+3.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -85,7 +86,9 @@ __device__ __forceinline__ uint32_t deq_pair(uint32_t magic_bits, __nv_bfloat162
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int N_MMA>
+// DBG: 0 = production; 1 = no dequant math (raw words to TMEM); 2 = math but no TMEM store;
+//      3 = dequant warps only recycle the stages (pure TMA/barrier pipeline).  Bring-up only.
+template <int N_MMA, int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_sz,
@@ -214,6 +217,15 @@ int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
       const int s = c % S, t = c % A_STAGES;
       const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
       mbar_wait(&wfull[s], (c / S) & 1);
+      if (DBG == 3) {
+        mbar_wait(&aempty[t], ((c / A_STAGES) & 1) ^ 1);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&afull[t]);
+          mbar_arrive(&sempty[s]);
+        }
+        continue;
+      }
 
       uint4 v[4];
 #pragma unroll
@@ -245,14 +257,21 @@ int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const uint32_t m = ((word >> (4 * e)) & 0x000F000Fu) | 0x43004300u;
-            out[16 * wd + i + 4 * e] = deq_pair(m, s2, z2);
+            out[16 * wd + i + 4 * e] = (DBG == 1) ? (word + e) : deq_pair(m, s2, z2);
           }
         }
       }
       const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
-      tmem_st_x32(a_t, out);
-      tmem_st_x32(a_t + 32, out + 32);
-      tc_wait_st();
+      if (DBG == 2) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) x ^= out[i];
+        if (x == 0x12345678u) p.ws_sem[1000 + threadIdx.x] = x;  // keep the math alive
+      } else {
+        tmem_st_x32(a_t, out);
+        tmem_st_x32(a_t + 32, out + 32);
+        tc_wait_st();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -380,7 +399,7 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
   }
 }
 
-template <int N_MMA>
+template <int N_MMA, int DBG = 0>
 static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, const uint16_t* sz,
                      int g, int N, const uint16_t* bias, uint16_t* y, int N_out, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
@@ -429,7 +448,7 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
     if (!ws || ws_bytes < need || (size_t)n_tiles * m_blocks * 4 > 64 * 1024)
       return fail(AO_ERR_WORKSPACE, "int4 linear: workspace too small (%zu < %zu)", ws_bytes, need);
   }
-  auto kern = int4_linear_tc_kernel<N_MMA>;
+  auto kern = int4_linear_tc_kernel<N_MMA, DBG>;
   static bool attr_set = false;
   if (!attr_set) {
     AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -468,6 +487,20 @@ extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const 
                          reinterpret_cast<const __nv_bfloat16*>(bias),
                          reinterpret_cast<__nv_bfloat16*>(y), M, N, N_out, K, group_size));
     return AO_OK;
+  }
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("AO_B200_INT4_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (dbg > 0 && M <= 32) {
+#define AO_DBG_CASE(NM, D)                                                                      \
+  if (dbg == D)                                                                                 \
+    return int4k::launch_tc<NM, D>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, \
+                                   workspace, workspace_bytes, st);
+    if (M <= 16) { AO_DBG_CASE(16, 1) AO_DBG_CASE(16, 2) AO_DBG_CASE(16, 3) }
+    else { AO_DBG_CASE(32, 1) AO_DBG_CASE(32, 2) AO_DBG_CASE(32, 3) }
+#undef AO_DBG_CASE
   }
   if (M <= 16)
     return int4k::launch_tc<16>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out,
