@@ -81,7 +81,7 @@ def build_torch_binding(force: bool = False) -> Path:
     src = CSRC / "torch_binding.cpp"
     if not src.exists():
         raise FileNotFoundError(src)
-    if not force and not _newer(out, [src, ROOT.parent / "include" / "ao_b200.h"]):
+    if not force and not _newer(out, [src, CSRC / "torch_binding_lowp.inc", ROOT.parent / "include" / "ao_b200.h", LIB / "libao_b200.so"]):
         return out
     inc = []
     for p in ce.include_paths():

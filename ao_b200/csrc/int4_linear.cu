@@ -87,7 +87,8 @@ __device__ __forceinline__ uint32_t deq_pair(uint32_t magic_bits, __nv_bfloat162
 }
 
 // DBG: 0 = production; 1 = no dequant math (raw words to TMEM); 2 = math but no TMEM store;
-//      3 = dequant warps only recycle the stages (pure TMA/barrier pipeline).  Bring-up only.
+//      3 = dequant warps only recycle the stages (pure TMA/barrier pipeline); 4 = 3 + no MMAs;
+//      5 = 3 + MMAs round-robin over 4 accumulators; 6 = 3 + one MMA per chunk.  Bring-up only.
 template <int N_MMA, int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
@@ -194,9 +195,12 @@ int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
         const uint32_t xb = smem_u32(smem + (size_t)s * C::STAGE_BYTES + W_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+          if (DBG == 4) break;
+          if (DBG == 6 && kk > 0) break;
           const uint64_t bdesc = umma_desc_k_sw128(xb + (kk >> 2) * (N_MMA * 128) + (kk & 3) * 32);
           const uint32_t a_t = tmem_base + C::A_COL0 + t * A_COLS + kk * 8;
-          mma_ts_f16(tmem_base + C::D_COL, a_t, bdesc, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+          const uint32_t d_t = tmem_base + C::D_COL + (DBG == 5 ? (kk & 3) * N_MMA : 0);
+          mma_ts_f16(d_t, a_t, bdesc, idesc, (c > 0 || kk > (DBG == 5 ? 3 : 0)) ? 1u : 0u);
         }
         tc_commit(&aempty[t]);
         tc_commit(&sempty[s]);
@@ -217,7 +221,7 @@ int4_linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w,
       const int s = c % S, t = c % A_STAGES;
       const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
       mbar_wait(&wfull[s], (c / S) & 1);
-      if (DBG == 3) {
+      if (DBG >= 3) {
         mbar_wait(&aempty[t], ((c / A_STAGES) & 1) ^ 1);
         __syncwarp();
         if (lane == 0) {
@@ -498,8 +502,8 @@ extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const 
   if (dbg == D)                                                                                 \
     return int4k::launch_tc<NM, D>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, \
                                    workspace, workspace_bytes, st);
-    if (M <= 16) { AO_DBG_CASE(16, 1) AO_DBG_CASE(16, 2) AO_DBG_CASE(16, 3) }
-    else { AO_DBG_CASE(32, 1) AO_DBG_CASE(32, 2) AO_DBG_CASE(32, 3) }
+    if (M <= 16) { AO_DBG_CASE(16, 1) AO_DBG_CASE(16, 2) AO_DBG_CASE(16, 3) AO_DBG_CASE(16, 4) AO_DBG_CASE(16, 5) AO_DBG_CASE(16, 6) }
+    else { AO_DBG_CASE(32, 1) AO_DBG_CASE(32, 2) AO_DBG_CASE(32, 3) AO_DBG_CASE(32, 4) AO_DBG_CASE(32, 5) AO_DBG_CASE(32, 6) }
 #undef AO_DBG_CASE
   }
   if (M <= 16)

@@ -1,0 +1,282 @@
+// Dynamic activation quantisation prologues (bit-exact restatements of the reference's torch
+// ops, one fused kernel each instead of the 2-6 eager kernels the reference launches):
+//   int8 per-token symmetric : Int8Tensor.from_hp(x, PerRow())  int8_tensor.py:176-248,
+//                              quant_primitives.py:1487-1583 / :424-485
+//   e4m3 per-token           : _choose_scale_float8 + _quantize_affine_float8
+//                              quant_primitives.py:2172-2287 (float8_tensor.py:235-242)
+//   mxfp8 RCEIL block-32     : to_mx  mx_formats/mx_tensor.py:228-409, :111-225
+//   nvfp4 block-16           : nvfp4_quantize  mx_formats/nvfp4_tensor.py:772-854
+// and the 128x4 -> 32x16 scale swizzle (mx_formats/utils.py:31-70) fused into the writers.
+// Inputs are bf16 [M,K]; HBM-bound elementwise/reduction work: 16-byte vector loads, one
+// pass for the reduction and one for the cast (the row stays in L1/L2).
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
+#include "common.h"
+
+namespace ao {
+
+__device__ __forceinline__ float bf16_round(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = (l < nw) ? sh[l] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  return v;
+}
+// NaN-propagating abs-max like torch.amax(abs(x))
+__device__ __forceinline__ float nanmax(float a, float b) {
+  return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
+}
+
+// ---------------------------------------------------------------- int8 / fp8 rowwise
+template <int MODE>  // 0 = int8, 1 = e4m3
+__global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            int K, uint8_t* __restrict__ q,
+                                                            float* __restrict__ scale) {
+  __shared__ float sh[8];
+  const int m = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+  const int nv = K / 8;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 v = xr[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  amax = block_reduce_max(amax, sh);
+  float s;
+  if (MODE == 0) {
+    s = bf16_round(amax / 127.5f);                 // division happens in the input dtype (bf16)
+    s = fmaxf(s, 1.1920928955078125e-07f);         // eps = finfo(float32).eps
+  } else {
+    s = bf16_round(amax / 448.0f);                 // no eps (reference has none)
+  }
+  if (threadIdx.x == 0) scale[m] = s;
+  const float inv = 1.0f / s;
+  uint2* qr = reinterpret_cast<uint2*>(q + (size_t)m * K);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 v = xr[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint8_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      if (MODE == 0) {
+        const float a = fminf(fmaxf(rintf(f.x * inv), -128.f), 127.f);
+        const float b = fminf(fmaxf(rintf(f.y * inv), -128.f), 127.f);
+        o[2 * j] = (uint8_t)(int8_t)(int)a;
+        o[2 * j + 1] = (uint8_t)(int8_t)(int)b;
+      } else {
+        float a = f.x / s, b = f.y / s;
+        a = fminf(fmaxf(a, -448.f), 448.f);  // fminf/fmaxf drop NaN like torch.clamp? no: keep NaN
+        b = fminf(fmaxf(b, -448.f), 448.f);
+        if (s == 0.f) { a = __int_as_float(0x7fc00000); b = a; }  // 0/0 = NaN in the reference
+        o[2 * j] = (uint8_t)__nv_cvt_float_to_fp8(a, __NV_SATFINITE, __NV_E4M3);
+        o[2 * j + 1] = (uint8_t)__nv_cvt_float_to_fp8(b, __NV_SATFINITE, __NV_E4M3);
+      }
+    }
+    qr[i] = *reinterpret_cast<const uint2*>(o);
+  }
+}
+
+// ---------------------------------------------------------------- block-scaled formats
+__device__ __forceinline__ size_t blocked_index(int r, int c, int col_blocks) {
+  // mx_formats/utils.py:31-70: tile (r/128, c/4) of 512 bytes; (r%32)*16 + ((r%128)/32)*4 + c%4
+  return ((size_t)(r >> 7) * col_blocks + (c >> 2)) * 512 + (r & 31) * 16 + ((r & 127) >> 5) * 4 + (c & 3);
+}
+
+__device__ __forceinline__ uint8_t e8m0_rceil(float v) {
+  const uint32_t u = __float_as_uint(v);
+  if (!isfinite(v)) return 0xff;
+  const uint32_t be = (u >> 23) & 0xff, man = u & 0x7fffff;
+  const uint32_t up = (be == 0) ? (man > 0x400000u) : (man != 0);
+  return (uint8_t)(be + up);
+}
+__device__ __forceinline__ float e8m0_recip(uint8_t e) {
+  const uint8_t r = (uint8_t)(254 - (int)e);
+  uint32_t bits = (uint32_t)r << 23;
+  if (r == 0) bits = 0x00400000u;
+  if (r == 0xff) bits = 0x7f800001u;
+  return __uint_as_float(bits);
+}
+
+// one thread per 32-element block
+__global__ void mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
+                                   uint8_t* __restrict__ q, uint8_t* __restrict__ sc, int swizzled) {
+  const int nb = K / 32;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * nb) return;
+  const int m = idx / nb, kb = idx % nb;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * K + kb * 32);
+  uint4 v[4];
+  float f[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = src[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      f[i * 8 + 2 * j] = t.x;
+      f[i * 8 + 2 * j + 1] = t.y;
+      amax = nanmax(amax, nanmax(fabsf(t.x), fabsf(t.y)));
+    }
+  }
+  const float inv448 = (float)(1.0 / 448.0);
+  const uint8_t e = e8m0_rceil(amax * inv448);
+  const float r = e8m0_recip(e);
+  if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e;
+  else sc[(size_t)m * nb + kb] = e;
+  uint8_t o[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) o[i] = (uint8_t)__nv_cvt_float_to_fp8(f[i] * r, __NV_SATFINITE, __NV_E4M3);
+  uint4* dst = reinterpret_cast<uint4*>(q + (size_t)m * K + kb * 32);
+  dst[0] = reinterpret_cast<const uint4*>(o)[0];
+  dst[1] = reinterpret_cast<const uint4*>(o)[1];
+}
+
+// e2m1 RNE, saturating (custom_fp_utils.py:27-146): thresholds are the midpoints, ties to even
+__device__ __forceinline__ uint32_t f32_to_e2m1(float f) {
+  const uint32_t s = (__float_as_uint(f) >> 31) << 3;
+  const float a = fabsf(f);
+  uint32_t c;
+  if (!(a < 5.0f)) c = (a == 5.0f) ? 6 : 7;        // 5.0 ties to 4 (code 6, even); NaN -> 7
+  else if (a >= 3.5f) c = 6;                        // 3.5 ties to 4
+  else if (a > 2.5f) c = 5;                         // 2.5 ties to 2 (code 4)
+  else if (a >= 1.75f) c = 4;                       // 1.75 ties to 2
+  else if (a > 1.25f) c = 3;                        // 1.25 ties to 1
+  else if (a >= 0.75f) c = 2;                       // 0.75 ties to 1
+  else if (a > 0.25f) c = 1;                        // 0.25 ties to 0
+  else c = 0;
+  return s | c;
+}
+
+// one thread per 16-element block
+__global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
+                                   const float* __restrict__ pts, uint8_t* __restrict__ q,
+                                   uint8_t* __restrict__ sc, int swizzled) {
+  const int nb = K / 16;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * nb) return;
+  const int m = idx / nb, kb = idx % nb;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * K + kb * 16);
+  float f[16];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 v = src[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      f[i * 8 + 2 * j] = t.x;
+      f[i * 8 + 2 * j + 1] = t.y;
+      amax = fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y)));
+    }
+  }
+  const float bs = amax / 6.0f;
+  float recip;
+  uint8_t b8;
+  if (pts == nullptr) {
+    const float c = fminf(fmaxf(bs, 0.015625f), 448.f);
+    b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
+    const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
+    recip = 1.0f / bf;
+  } else {
+    const float p = *pts;
+    const float c = fminf(fmaxf(bs / p, 0.015625f), 448.f);
+    b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
+    const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
+    recip = (1.0f / p) / bf;
+  }
+  if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
+  else sc[(size_t)m * nb + kb] = b8;
+  uint8_t o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = f[2 * i] * recip, b = f[2 * i + 1] * recip;
+    a = fminf(fmaxf(a, -6.f), 6.f);
+    b = fminf(fmaxf(b, -6.f), 6.f);
+    o[i] = (uint8_t)(f32_to_e2m1(a) | (f32_to_e2m1(b) << 4));  // even k in the LOW nibble
+  }
+  *reinterpret_cast<uint2*>(q + (size_t)m * (K / 2) + kb * 8) = *reinterpret_cast<const uint2*>(o);
+}
+
+__global__ void zero_bytes_kernel(uint8_t* p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+}  // namespace ao
+
+using namespace ao;
+
+extern "C" int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t* q, float* scale,
+                                        void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "int8 quantize: bad sizes M=%d K=%d (K%%8==0)", M, K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && q && scale, "int8 quantize: null pointer");
+  AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<0>, dim3(M), dim3(256), 0,
+                           reinterpret_cast<cudaStream_t>(stream), false,
+                           reinterpret_cast<const __nv_bfloat16*>(x), K, reinterpret_cast<uint8_t*>(q), scale));
+  return AO_OK;
+}
+
+extern "C" int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t* q, float* scale,
+                                       void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "fp8 quantize: bad sizes M=%d K=%d (K%%8==0)", M, K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && q && scale, "fp8 quantize: null pointer");
+  AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<1>, dim3(M), dim3(256), 0,
+                           reinterpret_cast<cudaStream_t>(stream), false,
+                           reinterpret_cast<const __nv_bfloat16*>(x), K, q, scale));
+  return AO_OK;
+}
+
+extern "C" int ao_mxfp8_quantize(const uint16_t* x, int M, int K, uint8_t* q, uint8_t* scale_e8m0,
+                                 int swizzled, void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 32 == 0, "mxfp8 quantize: K=%d must be a multiple of 32 (mx_tensor.py:244-246)", K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && q && scale_e8m0, "mxfp8 quantize: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nb = K / 32;
+  if (swizzled) {
+    const size_t bytes = (size_t)ceil_div(M, 128) * ceil_div(nb, 4) * 512;
+    if (M % 128 != 0 || nb % 4 != 0)
+      AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e8m0, bytes));
+  }
+  const size_t total = (size_t)M * nb;
+  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, false,
+                           reinterpret_cast<const __nv_bfloat16*>(x), M, K, q, scale_e8m0, swizzled));
+  return AO_OK;
+}
+
+extern "C" int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* per_tensor_scale,
+                                 uint8_t* q, uint8_t* scale_e4m3, int swizzled, void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 16 == 0, "nvfp4 quantize: K=%d must be a multiple of 16", K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && q && scale_e4m3, "nvfp4 quantize: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nb = K / 16;
+  if (swizzled) {
+    const size_t bytes = (size_t)ceil_div(M, 128) * ceil_div(nb, 4) * 512;
+    if (M % 128 != 0 || nb % 4 != 0)
+      AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e4m3, bytes));
+  }
+  const size_t total = (size_t)M * nb;
+  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, false,
+                           reinterpret_cast<const __nv_bfloat16*>(x), M, K, per_tensor_scale, q, scale_e4m3, swizzled));
+  return AO_OK;
+}

@@ -44,7 +44,7 @@ def time_graph(fn, iters=5):
 def sweep(ops):
     g = 32
     copies = 24
-    shapes = [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (14336, 1024), (14336, 2048), (14336, 8192), (128, 1024), (18944, 4096)]
+    shapes = [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (14336, 2048), (14336, 8192)]
     print(f"DBG={os.environ.get('AO_B200_INT4_DBG','0')} NO_PDL={os.environ.get('AO_B200_NO_PDL','0')}")
     for M in (1, 32):
         for (N, K) in shapes:
@@ -80,10 +80,9 @@ def ncu_stage(ops):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sweep"
     if mode == "all":
-        for pdl in ("0", "1"):
-            for dbg in ("0", "1", "2", "3"):
-                if pdl == "1" and dbg != "0":
-                    continue
+        dbgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "2", "3"]
+        for pdl in ("0",):
+            for dbg in dbgs:
                 env = dict(os.environ, AO_B200_INT4_DBG=dbg, AO_B200_NO_PDL=pdl)
                 try:
                     r = subprocess.run([sys.executable, os.path.abspath(__file__), "sweep"], env=env, timeout=300,
