@@ -28,3 +28,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def _ensure_native_built():
+    """The native libs are git-ignored build products; (re)build them before the first import."""
+    from ao_b200 import _build
+
+    _build.build_all()
+    from oracle import oracle as o
+
+    o.build()
+
+
+_ensure_native_built()
