@@ -1,0 +1,199 @@
+// NVFP4 weight (e2m1 + e4m3 block-16 scales + f32 per-tensor scale) x bf16 activation linear.
+//
+// Semantics = F.linear(x, NVFP4Tensor.dequantize()) (torchao/prototype/mx_formats/nvfp4_tensor.py:199-231,
+// weight-only handler inference_workflow.py:356-400), with an optional per-token activation scale applied in
+// the epilogue so that e4m3-rowwise-quantised activations (BASELINE config 5) run on the
+// same kernel: their values are exact in bf16, the scale is a row factor.
+// tcgen05 has no nvfp4 x bf16/fp8 MMA kind, so the weights are dequantised in-kernel to bf16 (exact: 2
+// significant bits x 4 significant bits) and fed from TMEM exactly like the int4 path (ts_gemm.cuh); the
+// per-tensor scale is applied in fp32 in the epilogue.
+//
+// e2m1 -> bf16 without a table: nibble x = (s e1 e0 m) placed at bf16 bits 15|8:6 is the bf16 number
+// value(x) * 2^-126 (denormal for e = 0, which bf16 multiplies handle exactly); one exact multiply by 2^120
+// and one by (block_scale * 2^6) give value(x) * block_scale.  bf16(block_scale * 64) = (byte << 4) + 0x3F00
+// for the (always normal, >= 2^-6) e4m3 scale bytes.
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "ts_gemm.cuh"
+
+namespace ao {
+namespace nvf4w {
+
+using tsg::KCHUNK;
+using tsg::ROWS;
+using tsg::W_BYTES;
+
+struct Nvfp4Fmt {
+  __device__ static __forceinline__ uint32_t w_tx_bytes(const tsg::Params&) { return W_BYTES + 1024; }
+  __device__ static __forceinline__ void issue_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p,
+                                                 uint8_t* w_dst, uint8_t* aux_dst, uint64_t* bar, int n_tile, int kc,
+                                                 uint64_t policy) {
+    tma_load_2d(w_dst, tm_w, bar, kc * 64, n_tile * ROWS, policy);  // 128 rows x 64 bytes, 64B swizzle
+    // two consecutive blocked scale tiles (128 rows x 4 scales each = 64 k per tile)
+    const uint8_t* src = p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(aux_dst)),
+                 "l"(src), "r"(1024), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  __device__ static __forceinline__ void dequant(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
+                                                 uint32_t (&out)[64]) {
+    uint4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = (uint32_t)r * 64u + i * 16;
+      v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 3) << 4)));  // undo the TMA 64B swizzle
+    }
+    // 8 scale bytes of this row: blocked tile j holds k-blocks 4j..4j+3
+    const uint32_t sc_off = (uint32_t)(r & 31) * 16u + (uint32_t)(r >> 5) * 4u;
+    const uint32_t sc[2] = {tsg::lds32(aux_smem + sc_off), tsg::lds32(aux_smem + 512 + sc_off)};
+    const uint32_t two120 = 0x7B807B80u;  // bf16x2 of 2^120
+    const __nv_bfloat162 c120 = *reinterpret_cast<const __nv_bfloat162*>(&two120);
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {  // word w = bytes 4w..4w+3 = k 8w..8w+7; scale block = w/2
+      const uint32_t word = (w & 3) == 0 ? v[w >> 2].x : (w & 3) == 1 ? v[w >> 2].y : (w & 3) == 2 ? v[w >> 2].z : v[w >> 2].w;
+      const uint32_t sb = (sc[w >> 3] >> (8 * ((w >> 1) & 3))) & 0xFFu;
+      const uint32_t s_bits = ((sb << 4) + 0x3F00u) * 0x00010001u;  // bf16x2 of scale * 2^6
+      const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t = word >> (8 * j);
+        const uint32_t h = (t & 0xFu) | ((t << 12) & 0xF0000u);       // even k -> low half, odd k -> high half
+        const uint32_t bits = (h * 0x1040u) & 0x81C081C0u;            // sign | e1 e0 m at bf16 bits 15 | 8:6
+        __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&bits);
+        x = __hmul2(x, c120);
+        x = __hmul2(x, s2);
+        out[4 * w + j] = *reinterpret_cast<uint32_t*>(&x);
+      }
+    }
+  }
+};
+
+template <int N_MMA>
+static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, const uint8_t* wq, const uint8_t* w_sf,
+                     const float* b_pts, int N, const uint16_t* bias, uint16_t* y, void* ws, size_t ws_bytes,
+                     cudaStream_t stream) {
+  using C = tsg::Cfg<N_MMA>;
+  CUtensorMap tm_w, tm_x;
+  {
+    const uint64_t dims[2] = {(uint64_t)K / 2, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)K / 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wq, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {64, (uint32_t)N_MMA};
+    int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  tsg::Params p{};
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.row_scale = x_scale;
+  p.out_scale = b_pts;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.ws_sem = reinterpret_cast<unsigned int*>(ws);
+  p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 64 * 1024);
+  p.aux_base = w_sf;
+  p.aux_col_blocks = ceil_div(K / 16, 4);
+  p.M = M; p.N = N; p.N_out = N; p.K = K; p.group_size = 16;
+  p.n_tiles = ceil_div(N, ROWS);
+  p.m_blocks = ceil_div(M, N_MMA);
+  p.KT = K / 128;
+  const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
+  int grid = sm_count();
+  if (units < grid) grid = (int)units;
+  const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
+  if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)
+    return fail(AO_ERR_WORKSPACE, "nvfp4 weight linear: workspace too small (%zu < %zu)", ws_bytes, need);
+  auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, N_MMA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+  return AO_OK;
+}
+
+// per-token e4m3 "fake quantisation": x -> bf16(e4m3(x / s)) and s = f32(bf16(amax/448)); the bf16 values
+// are exactly the e4m3 codes Float8Tensor.from_hp(x, PerRow()) would store (quant_primitives.py:2172-2287).
+__global__ void __launch_bounds__(256) fp8_fakequant_rowwise_kernel(const __nv_bfloat16* __restrict__ x, int K,
+                                                                    __nv_bfloat16* __restrict__ xq,
+                                                                    float* __restrict__ scale) {
+  __shared__ float sh[8];
+  const int m = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+  const int nv = K / 8;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 v = xr[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = sh[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) amax = fmaxf(amax, sh[i]);
+  const float s = __bfloat162float(__float2bfloat16_rn(amax / 448.0f));
+  if (threadIdx.x == 0) scale[m] = s;
+  uint4* qr = reinterpret_cast<uint4*>(xq + (size_t)m * K);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 v = xr[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      float a = fminf(fmaxf(f.x / s, -448.f), 448.f), b = fminf(fmaxf(f.y / s, -448.f), 448.f);
+      if (s == 0.f) { a = 0.f; b = 0.f; }  // all-zero row: the reference yields NaN (0/0); we keep zeros
+      const __nv_fp8_storage_t qa = __nv_cvt_float_to_fp8(a, __NV_SATFINITE, __NV_E4M3);
+      const __nv_fp8_storage_t qb = __nv_cvt_float_to_fp8(b, __NV_SATFINITE, __NV_E4M3);
+      o[2 * j] = __float2bfloat16_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(qa, __NV_E4M3))));
+      o[2 * j + 1] = __float2bfloat16_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(qb, __NV_E4M3))));
+    }
+    qr[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+}  // namespace nvf4w
+}  // namespace ao
+
+using namespace ao;
+
+extern "C" int ao_fp8_fakequant_rowwise(const uint16_t* x, int M, int K, uint16_t* xq_bf16, float* scale,
+                                        void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "fp8 fakequant: bad sizes M=%d K=%d", M, K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && xq_bf16 && scale, "fp8 fakequant: null pointer");
+  AO_CUDA_CHECK(ao::launch(nvf4w::fp8_fakequant_rowwise_kernel, dim3(M), dim3(256), 0,
+                           reinterpret_cast<cudaStream_t>(stream), false, reinterpret_cast<const __nv_bfloat16*>(x), K,
+                           reinterpret_cast<__nv_bfloat16*>(xq_bf16), scale));
+  return AO_OK;
+}
+
+extern "C" int ao_nvfp4_weight_linear(const uint16_t* x, const float* x_scale, int M, int K, const uint8_t* wq,
+                                      const uint8_t* w_scale_blocked, const float* b_pts, int N,
+                                      const uint16_t* bias, uint16_t* y, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && N > 0, "nvfp4 weight linear: bad sizes M=%d K=%d N=%d", M, K, N);
+  AO_REQUIRE(K % 128 == 0, "nvfp4 weight linear: K=%d must be a multiple of 128", K);
+  AO_REQUIRE(N % 16 == 0, "nvfp4 weight linear: N=%d must be a multiple of 16 (inference_workflow.py:248-251)", N);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && wq && w_scale_blocked && y, "nvfp4 weight linear: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 16) return nvf4w::launch_tc<16>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
+  if (M <= 32) return nvf4w::launch_tc<32>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
+  if (M <= 64) return nvf4w::launch_tc<64>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
+  return nvf4w::launch_tc<128>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
+}

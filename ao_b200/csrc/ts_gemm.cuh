@@ -1,0 +1,335 @@
+// Persistent "dequantise-into-TMEM" decode GEMM for sub-byte weights with bf16 activations (sm_100a).
+//
+//   Y[M,N] = X[M,K] * W^[N,K]^T (+bias),   W^ produced in-kernel from 4-bit weights + group scales
+//
+// Used by int4_linear.cu (tinygemm tile-packed int4, W^ = bf16((q-8)s+z)) and
+// nvfp4_weight_linear.cu (e2m1 * e4m3 block scale).  Structure:
+//   * swap-AB: 128 weight rows = UMMA M, tokens = UMMA N (16..128), fp32 accumulator in TMEM
+//   * persistent, one CTA per SM; the (n-tile, 128-k chunk) units of the whole GEMM are split EVENLY
+//     over the CTAs ("stream-K"), so every SM issues the same number of MMAs whatever N/K are
+//   * warps 0-3  : dequant warpgroup: ld.shared (conflict-free through the TMA swizzle) ->
+//                  unpack/scale in bf16x2 -> tcgen05.st of the A operand into TMEM (3 stages)
+//     warps 4-7  : epilogue: tcgen05.ld of a finished accumulator (double-buffered, overlaps the next
+//                  tile's MMAs), split-tile fix-up through an fp32 workspace, bias, bf16 store
+//     warp 8     : TMA producer (weights + scales + activations into a smem ring, mbarrier tx-count)
+//     warp 9     : MMA issuer: tcgen05.mma.kind::f16 A[tmem] x B[smem desc], tcgen05.commit
+//     (the kernel is tensor-core operand-ingest bound -- see DESIGN.md section 5 -- so one dequant
+//      warp per SM sub-partition is enough, and 320 threads x <=102 registers lets two CTAs co-reside)
+//   * tiles split across CTAs are reduced deterministically: every CTA writes its partial, bumps the
+//     tile's unit counter, and whoever completes the count sums the partials in CTA order
+//   * PDL: griddepcontrol.launch_dependents at start; weights are prefetched before
+//     griddepcontrol.wait, only activations / outputs / workspace wait for the previous kernel.
+//     Shared memory (~100 KB) and TMEM (256 columns) are sized so the next linear's CTA can
+//     co-reside with this one and start its own weight prefetch during our tail.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ao {
+namespace tsg {
+
+constexpr int ROWS = 128;
+constexpr int KCHUNK = 128;
+constexpr int W_BYTES = ROWS * KCHUNK / 2;  // 8 KiB of 4-bit weights per chunk
+constexpr int AUX_BYTES = 2048;             // scales per chunk (<= 2 KiB), 1 KiB aligned slot
+constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage (128 k / 2)
+constexpr int DEQ_WARPS = 4, EPI_WARP0 = 4, TMA_WARP = 8, MMA_WARP = 9;
+constexpr int NUM_THREADS = 10 * 32;
+
+template <int N_MMA>
+struct Cfg {
+  static constexpr int X_BYTES = 2 * N_MMA * 128;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES + AUX_BYTES;
+  static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 172 * 1024;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = N_MMA <= 64 ? 256 : 512;
+  static constexpr int D_COL0 = 0, D_COL1 = N_MMA;
+  static constexpr int A_COL0 = N_MMA <= 32 ? 64 : 2 * N_MMA;
+  static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 1024;
+};
+
+struct Params {
+  const __nv_bfloat16* bias;
+  const float* row_scale;   // optional per-token scale [M] applied in the epilogue (fp8 activations)
+  const float* out_scale;   // optional device scalar applied in the epilogue (nvfp4 per-tensor scale)
+  __nv_bfloat16* y;         // [M, N_out]
+  float* ws_partial;        // [grid][2][N_MMA*128]
+  unsigned int* ws_sem;     // [tiles]
+  const uint8_t* aux_base;  // format-specific scale base pointer (nvfp4: blocked scales)
+  int M, N, N_out, K, group_size;
+  int n_tiles, m_blocks, KT;   // KT = K/128
+  int aux_col_blocks;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// unit range of CTA b: [U*b/G, U*(b+1)/G)
+__device__ __forceinline__ int unit_begin(int b, long long U, int G) { return (int)((U * b) / G); }
+__device__ __forceinline__ int cta_of_unit(int u, long long U, int G) {
+  return (int)((((long long)(u + 1)) * G + U - 1) / U) - 1;
+}
+
+// Fmt policy:
+//   static void issue_w(tm_w, tm_aux, p, stage smem, full barrier, n0, kc, policy)   (one thread)
+//   static uint32_t w_tx_bytes(p)
+//   static void dequant(p, stage smem addr, row r, out[64])                          (128 threads)
+template <class Fmt, int N_MMA>
+__global__ void __launch_bounds__(NUM_THREADS, (N_MMA <= 64 ? 2 : 1))
+ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_aux,
+               const __grid_constant__ CUtensorMap tm_x, const Params p) {
+  using C = Cfg<N_MMA>;
+  constexpr int S = C::STAGES;
+  constexpr int T = C::A_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * C::STAGE_BYTES);
+  uint64_t* wfull = bars;             // [S]
+  uint64_t* xfull = wfull + S;        // [S]
+  uint64_t* sempty = xfull + S;       // [S]   4 dequant warps + MMA commit
+  uint64_t* afull = sempty + S;       // [T]
+  uint64_t* aempty = afull + T;       // [T]
+  uint64_t* dfull = aempty + T;       // [2]
+  uint64_t* dempty = dfull + 2;       // [2]   4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  uint32_t* flag_slot = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
+  const int u0 = unit_begin(b, U, G), u1 = unit_begin(b + 1, U, G);
+  const int nunits = u1 - u0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&xfull[i], 1);
+      mbar_init(&sempty[i], 5);  // 4 dequant warps + MMA commit
+    }
+    for (int i = 0; i < T; ++i) {
+      mbar_init(&afull[i], 4);
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_aux);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  // unit i of this CTA -> (tile, kc); tiles are (m_blk, n_tile) pairs, n_tile fastest
+  auto tile_of = [&](int i) { return (u0 + i) / p.KT; };
+  auto kc_of = [&](int i) { return (u0 + i) % p.KT; };
+
+  if (warp == TMA_WARP) {
+    if (lane == 0 && nunits > 0) {
+      const uint64_t pol_w = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      auto issue_w = [&](int i) {
+        const int s = i % S, tile = tile_of(i);
+        uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
+        mbar_expect_tx(&wfull[s], Fmt::w_tx_bytes(p));
+        Fmt::issue_w(&tm_w, &tm_aux, p, st, st + W_BYTES + C::X_BYTES, &wfull[s], tile % p.n_tiles, kc_of(i), pol_w);
+      };
+      auto issue_x = [&](int i) {
+        const int s = i % S, tile = tile_of(i);
+        uint8_t* st = smem + (size_t)s * C::STAGE_BYTES + W_BYTES;
+        const int m0 = (tile / p.n_tiles) * N_MMA, k0 = kc_of(i) * KCHUNK;
+        mbar_expect_tx(&xfull[s], C::X_BYTES);
+        tma_load_2d(st, &tm_x, &xfull[s], k0, m0, pol_x);
+        tma_load_2d(st + N_MMA * 128, &tm_x, &xfull[s], k0 + 64, m0, pol_x);
+      };
+      const int pre = nunits < S ? nunits : S;
+      for (int i = 0; i < pre; ++i) issue_w(i);  // weights never depend on the previous kernel
+      pdl_wait();
+      for (int i = 0; i < pre; ++i) issue_x(i);
+      for (int i = S; i < nunits; ++i) {
+        mbar_wait(&sempty[i % S], ((i / S) & 1) ^ 1);
+        issue_w(i);
+        issue_x(i);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);
+    int seg = 0;  // accumulator segment counter (one per tile touched)
+    for (int i = 0; i < nunits; ++i) {
+      const int s = i % S, t = i % T;
+      const bool first = (i == 0) || (kc_of(i) == 0);
+      const bool last = (i == nunits - 1) || (kc_of(i) == p.KT - 1);
+      const int buf = seg & 1;
+      if (first) {
+        mbar_wait(&dempty[buf], ((seg >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+      }
+      mbar_wait(&xfull[s], (i / S) & 1);
+      mbar_wait(&afull[t], (i / T) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xb = smem_u32(smem + (size_t)s * C::STAGE_BYTES + W_BYTES);
+        const uint32_t d_t = tmem_base + (buf ? C::D_COL1 : C::D_COL0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t bdesc = umma_desc_k_sw128(xb + (kk >> 2) * (N_MMA * 128) + (kk & 3) * 32);
+          mma_ts_f16(d_t, tmem_base + C::A_COL0 + t * A_COLS + kk * 8, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&aempty[t]);
+        tc_commit(&sempty[s]);
+        if (last) tc_commit(&dfull[buf]);
+      }
+      __syncwarp();
+      if (last) ++seg;
+    }
+  } else if (warp < DEQ_WARPS) {
+    // ------------------------------------------------------------ dequant warps
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    for (int i = 0; i < nunits; ++i) {
+      const int s = i % S, t = i % T;
+      const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+      mbar_wait(&wfull[s], (i / S) & 1);
+      uint32_t out[64];
+      Fmt::dequant(p, st, st + W_BYTES + C::X_BYTES, r, out);
+      mbar_wait(&aempty[t], ((i / T) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
+      tmem_st_x32(a_t, out);
+      tmem_st_x32(a_t + 32, out + 32);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&afull[t]);
+        mbar_arrive(&sempty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (4..7)
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    pdl_wait();
+    int seg = 0;
+    int i = 0;
+    while (i < nunits) {
+      const int tile = tile_of(i);
+      const int kc_first = kc_of(i);
+      int cnt = p.KT - kc_first;
+      if (cnt > nunits - i) cnt = nunits - i;
+      const int buf = seg & 1;
+      mbar_wait(&dfull[buf], (seg >> 1) & 1);
+      tc_fence_after();
+      const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
+      const uint32_t d_t = lane_taddr + (buf ? C::D_COL1 : C::D_COL0);
+      const float bias = (p.bias && n < p.N_out) ? __bfloat162float(p.bias[n]) : 0.f;
+      const float osc = p.out_scale ? *p.out_scale : 1.f;
+      if (cnt == p.KT) {
+        // the whole K range of this tile was ours: straight to the output
+#pragma unroll
+        for (int j = 0; j < N_MMA; j += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(d_t + j, rr);
+          tc_wait_ld();
+          if (n < p.N_out) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int m = m0 + j + q;
+              if (m < p.M) {
+                float v = __uint_as_float(rr[q]);
+                if (p.row_scale) v *= p.row_scale[m];
+                p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(v * osc + bias);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[buf]);
+      } else {
+        // tile shared with other CTAs: publish the partial, then see whether we complete the tile
+        const int which = (u0 / p.KT == tile) ? 0 : 1;
+        float* slot = p.ws_partial + ((size_t)b * 2 + which) * (N_MMA * ROWS);
+#pragma unroll
+        for (int j = 0; j < N_MMA; j += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(d_t + j, rr);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS + r], __uint_as_float(rr[q]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[buf]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == EPI_WARP0 * 32) {
+          const unsigned prev = atomicAdd(&p.ws_sem[tile], (unsigned)cnt);
+          *flag_slot = (prev + (unsigned)cnt == (unsigned)p.KT) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool finish = (*flag_slot != 0);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot is rewritten by the next segment
+        if (finish) {
+          __threadfence();
+          const int b_first = cta_of_unit(tile * p.KT, U, G);
+          const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
+          if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;  // restore for the next launch
+          if (n < p.N_out) {
+            for (int j = 0; j < N_MMA; ++j) {
+              const int m = m0 + j;
+              if (m >= p.M) break;
+              float v = 0.f;  // fixed CTA order => bit-reproducible whoever finishes
+              for (int bb = b_first; bb <= b_last; ++bb) {
+                const int wh = (unit_begin(bb, U, G) / p.KT == tile) ? 0 : 1;
+                v += __ldcg(&p.ws_partial[((size_t)bb * 2 + wh) * (N_MMA * ROWS) + j * ROWS + r]);
+              }
+              if (p.row_scale) v *= p.row_scale[m];
+              p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(v * osc + bias);
+            }
+          }
+        }
+      }
+      i += cnt;
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace tsg
+}  // namespace ao

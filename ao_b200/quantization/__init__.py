@@ -11,3 +11,9 @@ from .quant_api import (  # noqa: F401
 from .transform_module import register_quantize_module_handler  # noqa: F401
 from .utils import compute_error  # noqa: F401
 from ao_b200.float8.inference import Float8MMConfig  # noqa: F401
+
+import torch as _torch
+
+_torch.serialization.add_safe_globals([Granularity, PerAxis, PerBlock, PerGroup, PerRow, PerTensor, PerToken,
+                                       KernelPreference, MappingType, Int4PackingFormat, Int4ChooseQParamsAlgorithm,
+                                       Float8PackingFormat, Float8MMConfig])

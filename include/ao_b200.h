@@ -130,15 +130,20 @@ int ao_nvfp4_linear(const uint8_t* xq, const uint8_t* x_scale_blocked, const flo
                     int M, int K, const uint8_t* wq, const uint8_t* w_scale_blocked,
                     const float* b_pts, int N, const uint16_t* bias, uint16_t* y,
                     void* workspace, size_t workspace_bytes, void* stream);
-/* nvfp4 weight-only / nvfp4-weight x fp8-rowwise activation (BASELINE config 5):
- * y = bf16( sum_k A^[m,k] * dequant(W)[n,k] * x_scale[m] + bias ), where A^ is bf16
- * (act_fp8 == 0, x is bf16, x_scale ignored) or e4m3 (act_fp8 == 1).
+/* nvfp4 weight-only and nvfp4-weight x fp8-rowwise-activation (BASELINE config 5):
+ * y = bf16( (sum_k x[m,k] * e2m1(W)[n,k] * blockscale[n,k/16]) * x_scale[m] * b_pts + bias ),
+ * weights dequantised to bf16 inside the tcgen05 kernel.  x is bf16 [M,K]; x_scale f32 [M] or NULL.
  * Semantics = F.linear(x_dq, NVFP4Tensor.dequantize()) (nvfp4_tensor.py:199-231,
- * inference_workflow.py:356-400).                                                     */
-int ao_nvfp4_weight_linear(const void* x, const float* x_scale, int act_fp8, int M, int K,
+ * inference_workflow.py:356-400); for e4m3 activations pass the output of ao_fp8_fakequant_rowwise. */
+int ao_nvfp4_weight_linear(const uint16_t* x, const float* x_scale, int M, int K,
                            const uint8_t* wq, const uint8_t* w_scale_blocked,
                            const float* b_pts, int N, const uint16_t* bias, uint16_t* y,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Per-token e4m3 quantisation that keeps the codes as bf16 values (exact): xq = bf16(e4m3(x/s)),
+ * s = f32(bf16(amax/448)) -- the values Float8Tensor.from_hp(x, PerRow()) stores
+ * (quant_primitives.py:2172-2287), in the operand type the bf16 MMA consumes. */
+int ao_fp8_fakequant_rowwise(const uint16_t* x, int M, int K, uint16_t* xq_bf16, float* scale,
+                             void* stream);
 
 #ifdef __cplusplus
 }
