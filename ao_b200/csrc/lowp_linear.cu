@@ -239,45 +239,54 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       if (KIND == KIND_I8 || KIND == KIND_F8) sw = p.w_scale ? p.w_scale[n] : 1.f;
       if (KIND == KIND_NVF4) sw = (p.x_scale ? *p.x_scale : 1.f) * (p.w_scale ? *p.w_scale : 1.f);
       if (p.bias) bias = __bfloat162float(p.bias[n]);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < N_MMA; j += 16) {
+        if (m0 + j >= p.M) break;
         uint32_t rr[16];
+        float accf[16];
+        int32_t acci[16];
         if (p.splits == 1) {
           tmem_ld_x16(lane_taddr + j, rr);
           tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            acci[q] = (int32_t)rr[q];
+            accf[q] = __uint_as_float(rr[q]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            acci[q] = 0;
+            accf[q] = 0.f;
+          }
+          for (int sp = 0; sp < p.splits; ++sp) {  // fixed order: deterministic; 16 loads in flight
+            const uint32_t* src = base + (size_t)sp * (N_MMA * ROWS) + (size_t)j * ROWS + r;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const uint32_t v = __ldcg(src + q * ROWS);
+              acci[q] += (int32_t)v;
+              accf[q] += __uint_as_float(v);
+            }
+          }
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int m = m0 + j + q;
           if (m >= p.M) continue;
-          float accf;
-          int32_t acci = 0;
-          if (p.splits == 1) {
-            acci = (int32_t)rr[q];
-            accf = __uint_as_float(rr[q]);
-          } else {
-            float sf = 0.f;
-            for (int sp = 0; sp < p.splits; ++sp) {
-              const uint32_t v = __ldcg(&base[(size_t)sp * (N_MMA * ROWS) + (j + q) * ROWS + r]);
-              acci += (int32_t)v;
-              sf += __uint_as_float(v);
-            }
-            accf = sf;
-          }
           if (KIND == KIND_I8) {
             if (p.i32_out) {
-              p.i32_out[(size_t)m * p.N + n] = acci;
+              p.i32_out[(size_t)m * p.N + n] = acci[q];
               continue;
             }
             // int8/kernels.py:143-144 + int8_tensor.py:315-359: bf16 round between the scales
-            const float t = __bfloat162float(__float2bfloat16_rn((float)acci * p.x_scale[m]));
+            const float t = __bfloat162float(__float2bfloat16_rn((float)acci[q] * p.x_scale[m]));
             p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(t * sw + bias);
           } else if (KIND == KIND_F8) {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf * (p.x_scale[m] * sw) + bias);
+            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] * (p.x_scale[m] * sw) + bias);
           } else if (KIND == KIND_MXF8) {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf + bias);
+            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] + bias);
           } else {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf * sw + bias);
+            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] * sw + bias);
           }
         }
       }

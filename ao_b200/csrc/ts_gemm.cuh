@@ -304,16 +304,28 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
           if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;  // restore for the next launch
           if (n < p.N_out) {
-            for (int j = 0; j < N_MMA; ++j) {
-              const int m = m0 + j;
-              if (m >= p.M) break;
-              float v = 0.f;  // fixed CTA order => bit-reproducible whoever finishes
+            // fixed CTA order => bit-reproducible whoever finishes; 16 independent loads in flight per CTA slot
+#pragma unroll 1
+            for (int j0 = 0; j0 < N_MMA; j0 += 16) {
+              if (m0 + j0 >= p.M) break;
+              float v[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) v[q] = 0.f;
               for (int bb = b_first; bb <= b_last; ++bb) {
                 const int wh = (unit_begin(bb, U, G) / p.KT == tile) ? 0 : 1;
-                v += __ldcg(&p.ws_partial[((size_t)bb * 2 + wh) * (N_MMA * ROWS) + j * ROWS + r]);
+                const float* src = p.ws_partial + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + (size_t)j0 * ROWS + r;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] += __ldcg(src + q * ROWS);
               }
-              if (p.row_scale) v *= p.row_scale[m];
-              p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(v * osc + bias);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int m = m0 + j0 + q;
+                if (m < p.M) {
+                  float t = v[q];
+                  if (p.row_scale) t *= p.row_scale[m];
+                  p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(t * osc + bias);
+                }
+              }
             }
           }
         }

@@ -123,10 +123,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
     bcast_bytes = 0
     if world > 1:
-        for m in model.linear_modules():
-            for t in (m.weight.qdata, m.weight.scale_and_zero):
-                dist.broadcast(t, src=0)
-                bcast_bytes += t.numel() * t.element_size()
+        from ao_b200.parallel import broadcast_packed_weights
+
+        bcast_bytes = broadcast_packed_weights(model, src=0)  # the one collective of the whole job
         torch.cuda.synchronize()
 
     launch_count = torch.ops.ao_b200.launch_count
