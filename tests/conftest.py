@@ -31,13 +31,19 @@ def golden_dir():
 
 
 def _ensure_native_built():
-    """The native libs are git-ignored build products; (re)build them before the first import."""
-    from ao_b200 import _build
+    """The native libs are git-ignored build products.  Build them only when missing (on the GPU box the
+    prebuilt files travel with the snapshot; mtimes are not reliable there, so no staleness check)."""
+    import os
 
-    _build.build_all()
+    from ao_b200 import _build
+    from ao_b200._native import native_lib_paths
+
+    if not all(p.exists() for p in native_lib_paths()) or os.environ.get("AO_B200_FORCE_BUILD"):
+        _build.build_all(force=True)
     from oracle import oracle as o
 
-    o.build()
+    if not (o._DIR / "_build" / "libao_oracle.so").exists():
+        o.build()
 
 
 _ensure_native_built()
