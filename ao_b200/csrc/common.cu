@@ -71,6 +71,15 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+bool timeline_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_TIMELINE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

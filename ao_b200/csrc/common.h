@@ -65,6 +65,8 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // PDL can be disabled globally (AO_B200_NO_PDL=1) for debugging.
 bool pdl_enabled();
+// AO_B200_TIMELINE=1: kernels record per-CTA phase timestamps at workspace + 48 KiB (bring-up only).
+bool timeline_enabled();
 int sm_count();
 
 }  // namespace ao

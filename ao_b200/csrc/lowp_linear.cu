@@ -11,7 +11,8 @@
 // operand (N_MMA tokens).  TMA (SWIZZLE_128B) streams 128-byte-wide K blocks of W through a
 // deep smem ring straight into tcgen05.mma (SS mode) -- no register staging at all; block
 // scales go smem -> TMEM with tcgen05.cp.  Epilogue: TMEM -> registers -> scale/bias -> bf16.
-// Split-K across CTAs with a deterministic last-CTA reduction (int32 for int8: stays exact).
+// Persistent: one CTA per SM, (tile, K-chunk) units split evenly over the CTAs (stream-K); tiles shared by
+// several CTAs are reduced deterministically through a 32-bit workspace (int32 for int8: stays exact).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -24,10 +25,10 @@ namespace lowp {
 enum Kind { KIND_I8 = 0, KIND_F8 = 1, KIND_MXF8 = 2, KIND_NVF4 = 3 };
 
 constexpr int ROWS = 128;
-constexpr int KB = 128;  // bytes of K per stage per row (128 elems for 8-bit, 256 for fp4)
+constexpr int KB = 128;             // bytes of K per stage per row (128 elems for 8-bit, 256 for fp4)
 constexpr int A_BYTES = ROWS * KB;  // 16 KiB
-constexpr int NUM_THREADS = 192;    // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int MAX_SPLITS = 32;
+constexpr int EPI_WARP0 = 0, TMA_WARP = 4, MMA_WARP = 5;
+constexpr int NUM_THREADS = 192;
 
 template <int KIND, int N_MMA>
 struct Cfg {
@@ -37,14 +38,16 @@ struct Cfg {
   static constexpr int SF_TILES = KIND == KIND_MXF8 ? 1 : (KIND == KIND_NVF4 ? 4 : 0);
   static constexpr int SF_BYTES = SF_TILES * 512;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + 2 * SF_BYTES + (BLOCK_SCALED ? (1024 - (2 * SF_BYTES) % 1024) % 1024 : 0);
-  static constexpr int STAGES = (96 * 1024) / STAGE_BYTES < 3 ? 3 : ((96 * 1024) / STAGE_BYTES > 8 ? 8 : (96 * 1024) / STAGE_BYTES);
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 512;
-  // TMEM: D at [0, N_MMA); scale factors after it (double-buffered per stage parity)
-  static constexpr int SF_COLS = SF_TILES * 4;              // columns per operand per stage
-  static constexpr int SFA_COL = 128;                       // [128, 128 + 2*SF_COLS)
-  static constexpr int SFB_COL = 128 + 2 * 16;              // [160, 160 + 2*SF_COLS)
-  static constexpr int TMEM_COLS = BLOCK_SCALED ? 256 : (N_MMA <= 32 ? 32 : (N_MMA <= 64 ? 64 : 128));
-  static constexpr int MMA_PER_STAGE = 4;                   // K bytes per MMA = 32 (8-bit: 32 elems, fp4: 64)
+  static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 168 * 1024;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 1024;
+  // TMEM: two accumulators, then the scale factors (double-buffered by chunk parity)
+  static constexpr int D_COL0 = 0, D_COL1 = N_MMA;
+  static constexpr int SF_COLS = SF_TILES * 4;  // columns per operand per chunk
+  static constexpr int SFA_COL = N_MMA <= 64 ? 128 : 256;
+  static constexpr int SFB_COL = SFA_COL + 32;
+  static constexpr int TMEM_COLS = N_MMA <= 64 ? (BLOCK_SCALED ? 256 : (N_MMA <= 16 ? 32 : (N_MMA <= 32 ? 64 : 128))) : (BLOCK_SCALED ? 512 : 256);
+  static constexpr int MMA_PER_STAGE = 4;  // K bytes per MMA = 32 (8-bit: 32 elems, fp4: 64)
 };
 
 struct Params {
@@ -53,16 +56,23 @@ struct Params {
   const __nv_bfloat16* bias;
   __nv_bfloat16* y;       // bf16 out [M, N]  (null when i32_out is set)
   int32_t* i32_out;       // raw int32 accumulators [M, N] (ao_int8_mm_i32)
-  float* ws_partial;
-  unsigned int* ws_sem;
+  float* ws_partial;      // [grid][2][N_MMA*128] 32-bit partials (int32 bits for int8)
+  unsigned int* ws_sem;   // [tiles]
   int M, N, K;            // K in ELEMENTS
-  int splits;
+  int n_tiles, m_blocks, KT;  // KT = chunks of 128 K-bytes
   int sf_col_blocks_w;    // number of 4-wide scale column blocks per row block (blocked layout)
   int sf_col_blocks_x;
 };
 
+__device__ __forceinline__ int unit_begin(int b, long long U, int G) { return (int)((U * b) / G); }
+__device__ __forceinline__ int cta_of_unit(int u, long long U, int G) {
+  return (int)((((long long)(u + 1)) * G + U - 1) / U) - 1;
+}
+
+// Persistent stream-K kernel (same work split / fix-up protocol as ts_gemm.cuh, SS-mode MMAs):
+// warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.
 template <int KIND, int N_MMA>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, (N_MMA <= 64 ? 2 : 1))
 lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                    const uint8_t* __restrict__ w_sf, const uint8_t* __restrict__ x_sf,
                    const Params p) {
@@ -71,22 +81,21 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * C::STAGE_BYTES);
-  uint64_t* wfull = bars;            // weights (+ weight scales)
-  uint64_t* xfull = bars + S;        // activations (+ activation scales)
-  uint64_t* sempty = bars + 2 * S;   // MMA commit
-  uint64_t* dfull = bars + 3 * S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+  uint64_t* wfull = bars;            // [S] weights (+ weight scales)
+  uint64_t* xfull = wfull + S;       // [S] activations (+ activation scales)
+  uint64_t* sempty = xfull + S;      // [S] MMA commit
+  uint64_t* dfull = sempty + S;      // [2]
+  uint64_t* dempty = dfull + 2;      // [2] 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   uint32_t* flag_slot = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, split = blockIdx.y, m_blk = blockIdx.z;
-  const int n0 = n_tile * ROWS, m0 = m_blk * N_MMA;
-  constexpr int ELEMS_PER_BYTE = (KIND == KIND_NVF4) ? 2 : 1;
-  const int k_bytes = p.K / ELEMS_PER_BYTE;
-  const int total_chunks = k_bytes / KB;
-  const int c_begin = (int)(((long long)total_chunks * split) / p.splits);
-  const int c_end = (int)(((long long)total_chunks * (split + 1)) / p.splits);
-  const int nchunks = c_end - c_begin;
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
+  const int u0 = unit_begin(b, U, G), u1 = unit_begin(b + 1, U, G);
+  const int nunits = u1 - u0;
+  auto tile_of = [&](int i) { return (u0 + i) / p.KT; };
+  auto kc_of = [&](int i) { return (u0 + i) % p.KT; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
@@ -94,30 +103,32 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       mbar_init(&xfull[i], 1);
       mbar_init(&sempty[i], 1);
     }
-    mbar_init(dfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
-  if (warp == 0) {
+  if (warp == TMA_WARP) {
     if (lane == 0) {
       const uint64_t pol_w = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
-      auto issue_w = [&](int c) {
-        const int s = c % S;
+      auto issue_w = [&](int i) {
+        const int s = i % S, n_tile = tile_of(i) % p.n_tiles, kc = kc_of(i);
         uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
-        const int kc = c_begin + c;
         mbar_expect_tx(&wfull[s], A_BYTES + C::SF_BYTES);
-        tma_load_2d(st, &tm_w, &wfull[s], kc * (KB / (KIND == KIND_NVF4 ? 1 : 1)), n0, pol_w);
+        tma_load_2d(st, &tm_w, &wfull[s], kc * KB, n_tile * ROWS, pol_w);
         if (C::BLOCK_SCALED) {
           // blocked scale tiles of this (row block, k chunk): SF_TILES consecutive 512-byte tiles
           const uint8_t* src = w_sf + ((size_t)n_tile * p.sf_col_blocks_w + (size_t)kc * C::SF_TILES) * 512;
@@ -128,14 +139,13 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               : "memory");
         }
       };
-      auto issue_x = [&](int c) {
-        const int s = c % S;
+      auto issue_x = [&](int i) {
+        const int s = i % S, m0 = (tile_of(i) / p.n_tiles) * N_MMA, kc = kc_of(i);
         uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
-        const int kc = c_begin + c;
         mbar_expect_tx(&xfull[s], C::B_BYTES + C::SF_BYTES);
         tma_load_2d(st + A_BYTES, &tm_x, &xfull[s], kc * KB, m0, pol_x);
         if (C::BLOCK_SCALED) {
-          const uint8_t* src = x_sf + ((size_t)((m0 / 128)) * p.sf_col_blocks_x + (size_t)kc * C::SF_TILES) * 512;
+          const uint8_t* src = x_sf + ((size_t)(m0 / 128) * p.sf_col_blocks_x + (size_t)kc * C::SF_TILES) * 512;
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                   smem_u32(st + A_BYTES + C::B_BYTES + C::SF_BYTES)),
@@ -143,36 +153,44 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               : "memory");
         }
       };
-      const int pre = nchunks < S ? nchunks : S;
-      for (int c = 0; c < pre; ++c) issue_w(c);
+      const int pre = nunits < S ? nunits : S;
+      for (int i = 0; i < pre; ++i) issue_w(i);
       pdl_wait();
-      for (int c = 0; c < pre; ++c) issue_x(c);
-      for (int c = S; c < nchunks; ++c) {
-        mbar_wait(&sempty[c % S], ((c / S) & 1) ^ 1);
-        issue_w(c);
-        issue_x(c);
+      for (int i = 0; i < pre; ++i) issue_x(i);
+      for (int i = S; i < nunits; ++i) {
+        mbar_wait(&sempty[i % S], ((i / S) & 1) ^ 1);
+        issue_w(i);
+        issue_x(i);
       }
     }
-  } else if (warp == 1) {
-    // instruction descriptor per kind
+  } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc =
         KIND == KIND_I8   ? make_idesc(2 /*s32*/, 1 /*int8*/, 1 /*int8*/, ROWS, N_MMA)
         : KIND == KIND_F8 ? make_idesc(1 /*f32*/, 0 /*e4m3*/, 0 /*e4m3*/, ROWS, N_MMA)
         : KIND == KIND_MXF8 ? make_idesc_bs(0 /*e4m3*/, 0 /*e4m3*/, 1 /*ue8m0*/, ROWS, N_MMA)
                             : make_idesc_bs(1 /*e2m1*/, 1 /*e2m1*/, 0 /*ue4m3*/, ROWS, N_MMA);
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % S;
-      mbar_wait(&wfull[s], (c / S) & 1);
-      mbar_wait(&xfull[s], (c / S) & 1);
+    int seg = 0;
+    for (int i = 0; i < nunits; ++i) {
+      const int s = i % S;
+      const bool first = (i == 0) || (kc_of(i) == 0);
+      const bool last = (i == nunits - 1) || (kc_of(i) == p.KT - 1);
+      const int buf = seg & 1;
+      if (first) {
+        mbar_wait(&dempty[buf], ((seg >> 1) & 1) ^ 1);
+        tc_fence_after();
+      }
+      mbar_wait(&wfull[s], (i / S) & 1);
+      mbar_wait(&xfull[s], (i / S) & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t ab = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
         const uint32_t bb = ab + A_BYTES;
+        const uint32_t d_t = tmem_base + (buf ? C::D_COL1 : C::D_COL0);
         uint32_t sfa_t = 0, sfb_t = 0;
         if (C::BLOCK_SCALED) {
-          const int buf = c & 1;
-          sfa_t = tmem_base + C::SFA_COL + buf * C::SF_COLS;
-          sfb_t = tmem_base + C::SFB_COL + buf * C::SF_COLS;
+          const int sb = i & 1;
+          sfa_t = tmem_base + C::SFA_COL + sb * C::SF_COLS;
+          sfb_t = tmem_base + C::SFB_COL + sb * C::SF_COLS;
 #pragma unroll
           for (int tI = 0; tI < C::SF_TILES; ++tI) {
             // 512-byte tile = 32 rows x 16 bytes, contiguous: one 8x16B core matrix per 128 B
@@ -186,120 +204,144 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         for (int kk = 0; kk < C::MMA_PER_STAGE; ++kk) {
           const uint64_t adesc = umma_desc_k_sw128(ab + kk * 32);
           const uint64_t bdesc = umma_desc_k_sw128(bb + kk * 32);
-          const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-          if (KIND == KIND_I8) mma_ss_i8(tmem_base, adesc, bdesc, idesc, acc);
-          else if (KIND == KIND_F8) mma_ss_f8f6f4(tmem_base, adesc, bdesc, idesc, acc);
+          const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
+          if (KIND == KIND_I8) mma_ss_i8(d_t, adesc, bdesc, idesc, acc);
+          else if (KIND == KIND_F8) mma_ss_f8f6f4(d_t, adesc, bdesc, idesc, acc);
           else if (KIND == KIND_MXF8)
             // one scale byte per row per MMA: byte kk of the tile's column (sf_id fields)
-            mma_ss_mxf8f6f4(tmem_base, adesc, bdesc, idesc | ((uint32_t)kk << 29) | ((uint32_t)kk << 4), acc, sfa_t, sfb_t);
+            mma_ss_mxf8f6f4(d_t, adesc, bdesc, idesc | ((uint32_t)kk << 29) | ((uint32_t)kk << 4), acc, sfa_t, sfb_t);
           else
             // four scale bytes per row per MMA: tile kk
-            mma_ss_mxf4nvf4_b16(tmem_base, adesc, bdesc, idesc, acc, sfa_t + kk * 4, sfb_t + kk * 4);
+            mma_ss_mxf4nvf4_b16(d_t, adesc, bdesc, idesc, acc, sfa_t + kk * 4, sfb_t + kk * 4);
         }
         tc_commit(&sempty[s]);
-        if (c == nchunks - 1) tc_commit(dfull);
+        if (last) tc_commit(&dfull[buf]);
       }
       __syncwarp();
+      if (last) ++seg;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 0..3)
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
-    const int n = n0 + r;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     pdl_wait();
-    mbar_wait(dfull, 0);
-    tc_fence_after();
-    const int tile_lin = m_blk * gridDim.x + n_tile;
-    uint32_t* part = reinterpret_cast<uint32_t*>(p.ws_partial) + ((size_t)tile_lin * p.splits + split) * (N_MMA * ROWS);
-    bool last = true;
-    if (p.splits > 1) {
-#pragma unroll
-      for (int j = 0; j < N_MMA; j += 16) {
-        uint32_t rr[16];
-        tmem_ld_x16(lane_taddr + j, rr);
-        tc_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (m0 + j + q < p.M) __stcg(&part[(j + q) * ROWS + r], rr[q]);
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const unsigned prev = atomicAdd(&p.ws_sem[tile_lin], 1u);
-        *flag_slot = (prev == (unsigned)p.splits - 1) ? 1u : 0u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      last = (*flag_slot != 0);
-      if (last) __threadfence();
-    }
-    if (last && n < p.N) {
-      const uint32_t* base = reinterpret_cast<const uint32_t*>(p.ws_partial) + (size_t)tile_lin * p.splits * (N_MMA * ROWS);
+    int seg = 0, i = 0;
+    while (i < nunits) {
+      const int tile = tile_of(i);
+      int cnt = p.KT - kc_of(i);
+      if (cnt > nunits - i) cnt = nunits - i;
+      const int buf = seg & 1;
+      mbar_wait(&dfull[buf], (seg >> 1) & 1);
+      tc_fence_after();
+      const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
+      const uint32_t d_t = lane_taddr + (buf ? C::D_COL1 : C::D_COL0);
       float sw = 1.f, bias = 0.f;
-      if (KIND == KIND_I8 || KIND == KIND_F8) sw = p.w_scale ? p.w_scale[n] : 1.f;
-      if (KIND == KIND_NVF4) sw = (p.x_scale ? *p.x_scale : 1.f) * (p.w_scale ? *p.w_scale : 1.f);
-      if (p.bias) bias = __bfloat162float(p.bias[n]);
-#pragma unroll 1
-      for (int j = 0; j < N_MMA; j += 16) {
-        if (m0 + j >= p.M) break;
-        uint32_t rr[16];
-        float accf[16];
-        int32_t acci[16];
-        if (p.splits == 1) {
-          tmem_ld_x16(lane_taddr + j, rr);
+      if (n < p.N) {
+        if (KIND == KIND_I8 || KIND == KIND_F8) sw = p.w_scale ? p.w_scale[n] : 1.f;
+        if (KIND == KIND_NVF4) sw = (p.x_scale ? *p.x_scale : 1.f) * (p.w_scale ? *p.w_scale : 1.f);
+        if (p.bias) bias = __bfloat162float(p.bias[n]);
+      }
+      // finalise one accumulator value (raw 32 bits: s32 for int8, f32 otherwise) into the output
+      auto emit = [&](int m, uint32_t raw_i, float raw_f) {
+        if (KIND == KIND_I8) {
+          if (p.i32_out) {
+            p.i32_out[(size_t)m * p.N + n] = (int32_t)raw_i;
+            return;
+          }
+          // int8/kernels.py:143-144 + int8_tensor.py:315-359: bf16 round between the scales
+          const float t = __bfloat162float(__float2bfloat16_rn((float)(int32_t)raw_i * p.x_scale[m]));
+          p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(t * sw + bias);
+        } else if (KIND == KIND_F8) {
+          p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(raw_f * (p.x_scale[m] * sw) + bias);
+        } else if (KIND == KIND_MXF8) {
+          p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(raw_f + bias);
+        } else {
+          p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(raw_f * sw + bias);
+        }
+      };
+      if (cnt == p.KT) {
+#pragma unroll
+        for (int j = 0; j < N_MMA; j += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(d_t + j, rr);
+          tc_wait_ld();
+          if (n < p.N) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (m0 + j + q < p.M) emit(m0 + j + q, rr[q], __uint_as_float(rr[q]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[buf]);
+      } else {
+        const int which = (u0 / p.KT == tile) ? 0 : 1;
+        uint32_t* slot = reinterpret_cast<uint32_t*>(p.ws_partial) + ((size_t)b * 2 + which) * (N_MMA * ROWS);
+#pragma unroll
+        for (int j = 0; j < N_MMA; j += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(d_t + j, rr);
           tc_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            acci[q] = (int32_t)rr[q];
-            accf[q] = __uint_as_float(rr[q]);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            acci[q] = 0;
-            accf[q] = 0.f;
-          }
-          for (int sp = 0; sp < p.splits; ++sp) {  // fixed order: deterministic; 16 loads in flight
-            const uint32_t* src = base + (size_t)sp * (N_MMA * ROWS) + (size_t)j * ROWS + r;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const uint32_t v = __ldcg(src + q * ROWS);
-              acci[q] += (int32_t)v;
-              accf[q] += __uint_as_float(v);
-            }
-          }
+          for (int q = 0; q < 16; ++q)
+            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS + r], rr[q]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[buf]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == EPI_WARP0 * 32) {
+          const unsigned prev = atomicAdd(&p.ws_sem[tile], (unsigned)cnt);
+          *flag_slot = (prev + (unsigned)cnt == (unsigned)p.KT) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool finish = (*flag_slot != 0);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (finish) {
+          __threadfence();
+          const int b_first = cta_of_unit(tile * p.KT, U, G);
+          const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
+          if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;
+          if (n < p.N) {
+#pragma unroll 1
+            for (int j0 = 0; j0 < N_MMA; j0 += 16) {
+              if (m0 + j0 >= p.M) break;
+              float vf[16];
+              int32_t vi[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int m = m0 + j + q;
-          if (m >= p.M) continue;
-          if (KIND == KIND_I8) {
-            if (p.i32_out) {
-              p.i32_out[(size_t)m * p.N + n] = acci[q];
-              continue;
+              for (int q = 0; q < 16; ++q) {
+                vf[q] = 0.f;
+                vi[q] = 0;
+              }
+              for (int bb = b_first; bb <= b_last; ++bb) {  // fixed order: deterministic
+                const int wh = (unit_begin(bb, U, G) / p.KT == tile) ? 0 : 1;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.ws_partial) +
+                                      ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + (size_t)j0 * ROWS + r;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const uint32_t v = __ldcg(src + q * ROWS);
+                  vi[q] += (int32_t)v;
+                  vf[q] += __uint_as_float(v);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (m0 + j0 + q < p.M) emit(m0 + j0 + q, (uint32_t)vi[q], vf[q]);
             }
-            // int8/kernels.py:143-144 + int8_tensor.py:315-359: bf16 round between the scales
-            const float t = __bfloat162float(__float2bfloat16_rn((float)acci[q] * p.x_scale[m]));
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(t * sw + bias);
-          } else if (KIND == KIND_F8) {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] * (p.x_scale[m] * sw) + bias);
-          } else if (KIND == KIND_MXF8) {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] + bias);
-          } else {
-            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(accf[q] * sw + bias);
           }
         }
       }
-    }
-    if (p.splits > 1 && last) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) p.ws_sem[tile_lin] = 0;
+      i += cnt;
+      ++seg;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
@@ -328,39 +370,35 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
     int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, xq, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  const int n_tiles = ceil_div(N, ROWS);
-  const int m_blocks = ceil_div(M, N_MMA);
-  const int total_chunks = k_bytes / KB;
-  int splits = (2 * sm_count()) / (n_tiles * m_blocks);
-  if (splits < 1) splits = 1;
-  if (splits > MAX_SPLITS) splits = MAX_SPLITS;
-  if (splits > total_chunks) splits = total_chunks;
-  // keep at least 4 chunks per split so the pipeline has something to stream
-  while (splits > 1 && total_chunks / splits < 4) --splits;
-  Params p;
+  Params p{};
   p.x_scale = x_scale; p.w_scale = w_scale;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.i32_out = i32_out;
   p.ws_sem = reinterpret_cast<unsigned int*>(ws);
   p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 64 * 1024);
-  p.M = M; p.N = N; p.K = K; p.splits = splits;
+  p.M = M; p.N = N; p.K = K;
+  p.n_tiles = ceil_div(N, ROWS);
+  p.m_blocks = ceil_div(M, N_MMA);
+  p.KT = k_bytes / KB;
   const int sf_per_row = KIND == KIND_MXF8 ? K / 32 : (KIND == KIND_NVF4 ? K / 16 : 0);
   p.sf_col_blocks_w = ceil_div(sf_per_row, 4);
   p.sf_col_blocks_x = ceil_div(sf_per_row, 4);
-  if (splits > 1) {
-    const size_t need = 64 * 1024 + (size_t)n_tiles * m_blocks * splits * N_MMA * ROWS * 4;
-    if (!ws || ws_bytes < need || (size_t)n_tiles * m_blocks * 4 > 64 * 1024)
-      return fail(AO_ERR_WORKSPACE, "lowp linear: workspace too small (%zu < %zu)", ws_bytes, need);
-  }
+  const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
+  // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
+  int grid = sm_count();
+  if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
+  const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
+  if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)
+    return fail(AO_ERR_WORKSPACE, "lowp linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = lowp_linear_kernel<KIND, N_MMA>;
   static bool attr_set = false;
   if (!attr_set) {
     AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
-  AO_CUDA_CHECK(ao::launch(kern, dim3(n_tiles, splits, m_blocks), dim3(NUM_THREADS), C::SMEM_BYTES, stream,
-                           pdl_enabled(), tm_w, tm_x, w_sf, x_sf, p));
+  AO_CUDA_CHECK(ao::launch(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_x,
+                           w_sf, x_sf, p));
   return AO_OK;
 }
 

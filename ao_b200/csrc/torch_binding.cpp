@@ -144,6 +144,7 @@ TORCH_LIBRARY(ao_b200, m) {
   m.def("int4_dequant_tile4d(Tensor qdata, Tensor scale_and_zero, int group_size) -> Tensor");
   m.def("int4_tilepacked_linear(Tensor x, Tensor qdata, int group_size, Tensor scale_and_zero, Tensor? bias, int n_out=0, int impl=0) -> Tensor");
   m.def("launch_count() -> int", []() -> int64_t { return (int64_t)ao_b200_launch_count(); });
+  m.def("debug_workspace(Tensor like) -> Tensor", [](const at::Tensor& like) { return workspace_for(like); });
   ao_b200_define_lowp(m);
 }
 

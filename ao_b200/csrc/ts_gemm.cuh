@@ -7,14 +7,15 @@
 //   * swap-AB: 128 weight rows = UMMA M, tokens = UMMA N (16..128), fp32 accumulator in TMEM
 //   * persistent, one CTA per SM; the (n-tile, 128-k chunk) units of the whole GEMM are split EVENLY
 //     over the CTAs ("stream-K"), so every SM issues the same number of MMAs whatever N/K are
-//   * warps 0-3  : dequant warpgroup: ld.shared (conflict-free through the TMA swizzle) ->
-//                  unpack/scale in bf16x2 -> tcgen05.st of the A operand into TMEM (3 stages)
-//     warps 4-7  : epilogue: tcgen05.ld of a finished accumulator (double-buffered, overlaps the next
+//   * warps 0-7  : two dequant warpgroups, each taking one 64-k half of every chunk: ld.shared
+//                  (conflict-free through the TMA swizzle) -> unpack/scale in bf16x2 -> tcgen05.st of
+//                  the A operand into TMEM (3 stages).  Two warps per SM sub-partition hide each other's
+//                  ld.shared / tcgen05.st latency; half a row-chunk per thread keeps registers <= 72 so
+//                  two CTAs (this linear's tail + the next linear's head) fit on one SM.
+//     warps 8-11 : epilogue: tcgen05.ld of a finished accumulator (double-buffered, overlaps the next
 //                  tile's MMAs), split-tile fix-up through an fp32 workspace, bias, bf16 store
-//     warp 8     : TMA producer (weights + scales + activations into a smem ring, mbarrier tx-count)
-//     warp 9     : MMA issuer: tcgen05.mma.kind::f16 A[tmem] x B[smem desc], tcgen05.commit
-//     (the kernel is tensor-core operand-ingest bound -- see DESIGN.md section 5 -- so one dequant
-//      warp per SM sub-partition is enough, and 320 threads x <=102 registers lets two CTAs co-reside)
+//     warp 12    : TMA producer (weights + scales + activations into a smem ring, mbarrier tx-count)
+//     warp 13    : MMA issuer: tcgen05.mma.kind::f16 A[tmem] x B[smem desc], tcgen05.commit
 //   * tiles split across CTAs are reduced deterministically: every CTA writes its partial, bumps the
 //     tile's unit counter, and whoever completes the count sums the partials in CTA order
 //   * PDL: griddepcontrol.launch_dependents at start; weights are prefetched before
@@ -35,8 +36,8 @@ constexpr int KCHUNK = 128;
 constexpr int W_BYTES = ROWS * KCHUNK / 2;  // 8 KiB of 4-bit weights per chunk
 constexpr int AUX_BYTES = 2048;             // scales per chunk (<= 2 KiB), 1 KiB aligned slot
 constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage (128 k / 2)
-constexpr int DEQ_WARPS = 4, EPI_WARP0 = 4, TMA_WARP = 8, MMA_WARP = 9;
-constexpr int NUM_THREADS = 10 * 32;
+constexpr int DEQ_WARPS = 8, EPI_WARP0 = 8, TMA_WARP = 12, MMA_WARP = 13;
+constexpr int NUM_THREADS = 14 * 32;
 
 template <int N_MMA>
 struct Cfg {
@@ -62,6 +63,7 @@ struct Params {
   int M, N, N_out, K, group_size;
   int n_tiles, m_blocks, KT;   // KT = K/128
   int aux_col_blocks;
+  unsigned long long* timeline;  // debug: per-CTA [8] timestamps (AO_B200_TIMELINE=1), else null
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -89,7 +91,7 @@ __device__ __forceinline__ int cta_of_unit(int u, long long U, int G) {
 // Fmt policy:
 //   static void issue_w(tm_w, tm_aux, p, stage smem, full barrier, n0, kc, policy)   (one thread)
 //   static uint32_t w_tx_bytes(p)
-//   static void dequant(p, stage smem addr, row r, out[64])                          (128 threads)
+//   static void dequant(p, w smem, aux smem, row r, k-half h, out[32])                (256 threads)
 template <class Fmt, int N_MMA>
 __global__ void __launch_bounds__(NUM_THREADS, (N_MMA <= 64 ? 2 : 1))
 ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_aux,
@@ -112,6 +114,15 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
+  const long long t_entry = clock64();
+  auto stamp = [&](int e) {
+    if (p.timeline) p.timeline[(size_t)b * 8 + e] = (unsigned long long)(clock64() - t_entry);
+  };
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.timeline[(size_t)b * 8] = gt;
+  }
   const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
   const int u0 = unit_begin(b, U, G), u1 = unit_begin(b + 1, U, G);
   const int nunits = u1 - u0;
@@ -120,10 +131,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     for (int i = 0; i < S; ++i) {
       mbar_init(&wfull[i], 1);
       mbar_init(&xfull[i], 1);
-      mbar_init(&sempty[i], 5);  // 4 dequant warps + MMA commit
+      mbar_init(&sempty[i], DEQ_WARPS + 1);  // dequant warps + MMA commit
     }
     for (int i = 0; i < T; ++i) {
-      mbar_init(&afull[i], 4);
+      mbar_init(&afull[i], DEQ_WARPS);
       mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -143,6 +154,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) stamp(1);
 
   // unit i of this CTA -> (tile, kc); tiles are (m_blk, n_tile) pairs, n_tile fastest
   auto tile_of = [&](int i) { return (u0 + i) / p.KT; };
@@ -169,6 +181,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       const int pre = nunits < S ? nunits : S;
       for (int i = 0; i < pre; ++i) issue_w(i);  // weights never depend on the previous kernel
       pdl_wait();
+      stamp(2);
       for (int i = 0; i < pre; ++i) issue_x(i);
       for (int i = S; i < nunits; ++i) {
         mbar_wait(&sempty[i % S], ((i / S) & 1) ^ 1);
@@ -192,6 +205,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_wait(&afull[t], (i / T) & 1);
       tc_fence_after();
       if (lane == 0) {
+        if (i == 0) stamp(4);
         const uint32_t xb = smem_u32(smem + (size_t)s * C::STAGE_BYTES + W_BYTES);
         const uint32_t d_t = tmem_base + (buf ? C::D_COL1 : C::D_COL0);
 #pragma unroll
@@ -202,26 +216,26 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         tc_commit(&aempty[t]);
         tc_commit(&sempty[s]);
         if (last) tc_commit(&dfull[buf]);
+        if (i == nunits - 1) stamp(5);
       }
       __syncwarp();
       if (last) ++seg;
     }
   } else if (warp < DEQ_WARPS) {
     // ------------------------------------------------------------ dequant warps
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;
+    const int half = warp >> 2, q4 = warp & 3;   // warpgroup = 64-k half of the chunk
+    const int r = q4 * 32 + lane;                 // weight row of the tile == TMEM lane
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     for (int i = 0; i < nunits; ++i) {
       const int s = i % S, t = i % T;
       const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
       mbar_wait(&wfull[s], (i / S) & 1);
-      uint32_t out[64];
-      Fmt::dequant(p, st, st + W_BYTES + C::X_BYTES, r, out);
+      if (i == 0 && warp == 0 && lane == 0) stamp(3);
+      uint32_t out[32];
+      Fmt::dequant(p, st, st + W_BYTES + C::X_BYTES, r, half, out);
       mbar_wait(&aempty[t], ((i / T) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
-      tmem_st_x32(a_t, out);
-      tmem_st_x32(a_t + 32, out + 32);
+      tmem_st_x32(lane_taddr + C::A_COL0 + t * A_COLS + half * 32, out);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -231,7 +245,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (4..7)
+    // ------------------------------------------------------------ epilogue warps (8..11)
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -244,8 +258,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       int cnt = p.KT - kc_first;
       if (cnt > nunits - i) cnt = nunits - i;
       const int buf = seg & 1;
-      mbar_wait(&dfull[buf], (seg >> 1) & 1);
+      while (!mbar_try_wait(&dfull[buf], (seg >> 1) & 1)) __nanosleep(200);  // long wait: do not steal issue slots
       tc_fence_after();
+      if (i + cnt >= nunits && threadIdx.x == EPI_WARP0 * 32) stamp(6);
       const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
       const uint32_t d_t = lane_taddr + (buf ? C::D_COL1 : C::D_COL0);
@@ -302,6 +317,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           __threadfence();
           const int b_first = cta_of_unit(tile * p.KT, U, G);
           const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
+          const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
           if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;  // restore for the next launch
           if (n < p.N_out) {
             // fixed CTA order => bit-reproducible whoever finishes; 16 independent loads in flight per CTA slot
@@ -312,7 +328,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 #pragma unroll
               for (int q = 0; q < 16; ++q) v[q] = 0.f;
               for (int bb = b_first; bb <= b_last; ++bb) {
-                const int wh = (unit_begin(bb, U, G) / p.KT == tile) ? 0 : 1;
+                // only the first contributor can have started in an earlier tile (then this is its tail slot)
+                const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
                 const float* src = p.ws_partial + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + (size_t)j0 * ROWS + r;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] += __ldcg(src + q * ROWS);
@@ -333,6 +350,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       i += cnt;
       ++seg;
     }
+    if (threadIdx.x == EPI_WARP0 * 32) stamp(7);
   }
 
   tc_fence_before();

@@ -264,3 +264,26 @@ def test_tensor_subclass_plumbing_on_cpu():
     sz = torch.zeros(32, 16, 2, dtype=torch.bfloat16)
     i4 = Int4TilePackedTo4dTensor(qd, sz, [1, 32], torch.Size([16, 1024]))
     assert i4.shape == (16, 1024) and i4[8:16].qdata.shape == (1, 8, 32, 4) and i4[8:16].scale_and_zero.shape == (32, 8, 2)
+
+
+def test_missing_native_library_fails_loudly(monkeypatch, tmp_path):
+    from ao_b200 import _native
+
+    monkeypatch.setattr(_native, "_LIB_DIR", tmp_path)
+    monkeypatch.setattr(_native, "_LOADED", False)
+    with pytest.raises(ImportError, match="native library not built"):
+        _native.load_native()
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under ao_b200/ may import, link or call it."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ao_b200")):
+        if os.path.basename(dirpath) in ("lib", "obj", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|ao_oracle|libao_oracle", txt, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
