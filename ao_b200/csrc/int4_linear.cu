@@ -48,34 +48,33 @@ struct Int4Fmt {
     tma_load_3d(w_dst, tm_w, bar, 0, 4 * kc, n_tile * (ROWS / 8), policy);
     tma_load_2d(aux_dst, tm_sz, bar, n_tile * ROWS, (kc * KCHUNK) / p.group_size, policy);
   }
-  // thread (row r, k-half h): 32 packed bytes (words 2h, 2h+1 of the row's four 16-byte lane chunks) + the
-  // (s,z) pairs of those two 32-k words -> 32 bf16x2 = TMEM columns [32h, 32h+32) of the A stage
+  // thread r (= TMEM lane = weight row of the tile): 64 packed bytes + up to 4 (s,z) pairs -> 64 bf16x2
   __device__ static __forceinline__ void dequant(const tsg::Params& p, uint32_t w_smem, uint32_t aux_smem, int r,
-                                                 int h, uint32_t (&out)[32]) {
+                                                 uint32_t (&out)[64]) {
     const uint32_t row_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u;
     const int gshift = p.group_size == 32 ? 0 : (p.group_size == 64 ? 1 : 2);  // word -> group
-    uint2 v[4];
+    uint4 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t off = row_off + i * 16;
-      v[i] = tsg::lds64(w_smem + (off ^ (((off >> 7) & 7) << 4)) + h * 8);  // undo the TMA 128B swizzle
+      v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 7) << 4)));  // undo the TMA 128B swizzle
     }
-    uint32_t sz[2];  // (s,z) of the group each 32-k word belongs to
+    uint32_t sz[4];  // (s,z) of the group each 32-k word belongs to
 #pragma unroll
-    for (int wl = 0; wl < 2; ++wl) sz[wl] = tsg::lds32(aux_smem + r * 4 + ((2 * h + wl) >> gshift) * 512);
+    for (int wd = 0; wd < 4; ++wd) sz[wd] = tsg::lds32(aux_smem + r * 4 + (wd >> gshift) * 512);
 #pragma unroll
-    for (int wl = 0; wl < 2; ++wl) {
-      const uint32_t s_bits = __byte_perm(sz[wl], sz[wl], 0x1010);
-      const uint32_t z_bits = __byte_perm(sz[wl], sz[wl], 0x3232);
+    for (int wd = 0; wd < 4; ++wd) {
+      const uint32_t s_bits = __byte_perm(sz[wd], sz[wd], 0x1010);
+      const uint32_t z_bits = __byte_perm(sz[wd], sz[wd], 0x3232);
       const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
       const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&z_bits);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t word = wl == 0 ? v[i].x : v[i].y;
+        const uint32_t word = (wd == 0) ? v[i].x : (wd == 1) ? v[i].y : (wd == 2) ? v[i].z : v[i].w;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t m = ((word >> (4 * e)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 of 128+q
-          out[16 * wl + i + 4 * e] = deq_pair(m, s2, z2);  // k pair (64h + 32wl + 2i + 8e, +1)
+          out[16 * wd + i + 4 * e] = deq_pair(m, s2, z2);                         // k pair (32wd+2i+8e, +1)
         }
       }
     }
@@ -180,11 +179,12 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)
     return fail(AO_ERR_WORKSPACE, "int4 linear: workspace too small (%zu < %zu)", ws_bytes, need);
-  auto kern = tsg::ts_gemm_kernel<Int4Fmt, N_MMA>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true>
+                                           : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[p.timeline ? 1 : 0]) {
     AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[p.timeline ? 1 : 0] = true;
   }
   AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_sz,
                        tm_x, p));

@@ -27,7 +27,7 @@ def read_tl(x, ncta):
 
 
 for M in (1, 32):
-    for (N, K) in [(14336, 4096), (4096, 4096), (1024, 4096), (4096, 14336)]:
+    for (N, K) in [(14336, 4096), (4096, 14336)]:
         x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         wa, wb = mk(N, K), mk(N, K)
         for back_to_back in (False, True):
@@ -51,5 +51,11 @@ for M in (1, 32):
             ph = tl[:, 1:].float()
             med = ph.median(dim=0).values.tolist()
             mx = ph.max(dim=0).values.tolist()
+            ws2 = ops.debug_workspace(x)
+            fine = ws2[48 * 1024 + 148 * 64: 48 * 1024 + 148 * 64 + 4 * 64].view(torch.int64).reshape(4, 8).cpu().tolist()
             print(f"M={M:2d} N={N:5d} K={K:5d} b2b={int(back_to_back)} ctas={int(used.sum())} total={e0.elapsed_time(e1)*1e3:7.1f}us "
                   f"entry_spread={(gt.max()-gt.min()).item()/1e3:5.2f}us  med(cyc)={[int(v) for v in med]}  max={[int(v) for v in mx]}")
+            if not back_to_back:
+                print("     units 8..11 of CTA0 [wfull, math_done, aempty_ok, st_done, arrived, mma_start, mma_issued]:")
+                for row in fine:
+                    print("      ", row[:7])
