@@ -80,6 +80,15 @@ bool timeline_enabled() {
   return v == 1;
 }
 
+int ts_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_TS_FLAGS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -67,6 +67,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 bool pdl_enabled();
 // AO_B200_TIMELINE=1: kernels record per-CTA phase timestamps at workspace + 48 KiB (bring-up only).
 bool timeline_enabled();
+int ts_flags();  // AO_B200_TS_FLAGS bring-up switches for ts_gemm.cuh
 int sm_count();
 
 }  // namespace ao

@@ -171,6 +171,7 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   p.n_tiles = ceil_div(N_out, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);
   p.KT = KT;
+  p.flags = ts_flags();
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
   const long long units = (long long)p.n_tiles * p.m_blocks * KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)

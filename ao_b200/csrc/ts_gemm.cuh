@@ -61,6 +61,7 @@ struct Params {
   int M, N, N_out, K, group_size;
   int n_tiles, m_blocks, KT;   // KT = K/128
   int aux_col_blocks;
+  int flags;  // bring-up switches (AO_B200_TS_FLAGS): 1 = dequant warpgroups on the high warp ids, 2 = sleep in TMA/MMA waits
   unsigned long long* timeline;  // debug: per-CTA [8] timestamps (AO_B200_TIMELINE=1), else null
 };
 
@@ -144,7 +145,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   uint32_t* flag_slot = tmem_slot + 1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // role (virtual) warp id; shifting by two warpgroups keeps the TMEM lane quarter (warp & 3) intact
+  const int warp = ((threadIdx.x >> 5) + ((p.flags & 1) ? 8 : 0)) & 15, lane = threadIdx.x & 31;
+  const bool nap = (p.flags & 2) != 0;
   const int G = gridDim.x, b = blockIdx.x;
   const long long t_entry = TL ? clock64() : 0;
   auto stamp = [&](int e) {
@@ -253,7 +256,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         stamp(2);
         for (int i = 0; i < pre; ++i) issue_x(i);
         for (int i = S; i < nunits; ++i) {
-          mbar_wait(&sempty[i % S], ((i / S) & 1) ^ 1);
+          while (!mbar_try_wait(&sempty[i % S], ((i / S) & 1) ^ 1)) { if (nap) __nanosleep(64); }
           issue_w(i);
           issue_x(i);
         }
@@ -269,8 +272,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         if (first) {
           mbar_wait(&dempty[buf], ((seg >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         }
-        mbar_wait(&xfull[s], (i / S) & 1);
-        mbar_wait(&afull[t], (i / T) & 1);
+        while (!mbar_try_wait(&xfull[s], (i / S) & 1)) { if (nap) __nanosleep(32); }
+        while (!mbar_try_wait(&afull[t], (i / T) & 1)) { if (nap) __nanosleep(32); }
         tc_fence_after();
         if (lane == 0) {
           if (i == 0) stamp(4);
@@ -305,7 +308,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       const int buf = seg & 1;
       while (!mbar_try_wait(&dfull[buf], (seg >> 1) & 1)) __nanosleep(200);  // long wait: do not steal issue slots
       tc_fence_after();
-      if (i + cnt >= nunits && threadIdx.x == EPI_WARP0 * 32) stamp(6);
+      if (i + cnt >= nunits && (warp == EPI_WARP0 && lane == 0)) stamp(6);
       const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
       const uint32_t d_t = lane_taddr + (buf ? C::D_COL1 : C::D_COL0);
@@ -357,7 +360,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         if (lane == 0) mbar_arrive(&dempty[buf]);
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == EPI_WARP0 * 32) {
+        if ((warp == EPI_WARP0 && lane == 0)) {
           const unsigned prev = atomicAdd(&p.ws_sem[tile], (unsigned)cnt);
           *flag_slot = (prev + (unsigned)cnt == (unsigned)p.KT) ? 1u : 0u;
         }
@@ -369,7 +372,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           const int b_first = cta_of_unit(tile * p.KT, U, G);
           const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
           const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
-          if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;  // restore for the next launch
+          if ((warp == EPI_WARP0 && lane == 0)) p.ws_sem[tile] = 0;  // restore for the next launch
           if (n < p.N_out) {
             // fixed CTA order => bit-reproducible whoever finishes; 8 independent loads in flight per CTA slot
 #pragma unroll 1
@@ -401,7 +404,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       i += cnt;
       ++seg;
     }
-    if (threadIdx.x == EPI_WARP0 * 32) stamp(7);
+    if ((warp == EPI_WARP0 && lane == 0)) stamp(7);
   }
 
   tc_fence_before();

@@ -26,8 +26,9 @@ def read_tl(x, ncta):
     return tl
 
 
-for M in (1, 32):
-    for (N, K) in [(14336, 4096), (4096, 14336)]:
+Ms = (1, 32) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split(','))
+for M in Ms:
+    for (N, K) in [(14336, 4096)]:
         x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         wa, wb = mk(N, K), mk(N, K)
         for back_to_back in (False, True):
