@@ -89,6 +89,16 @@ int ts_flags() {
   return v;
 }
 
+int ts_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_TS_CTAS_PER_SM");
+    v = e ? atoi(e) : 2;
+    if (v < 1 || v > 2) v = 2;
+  }
+  return v;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

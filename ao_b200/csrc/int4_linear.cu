@@ -48,33 +48,35 @@ struct Int4Fmt {
     tma_load_3d(w_dst, tm_w, bar, 0, 4 * kc, n_tile * (ROWS / 8), policy);
     tma_load_2d(aux_dst, tm_sz, bar, n_tile * ROWS, (kc * KCHUNK) / p.group_size, policy);
   }
-  // thread r (= TMEM lane = weight row of the tile): 64 packed bytes + up to 4 (s,z) pairs -> 64 bf16x2
-  __device__ static __forceinline__ void dequant(const tsg::Params& p, uint32_t w_smem, uint32_t aux_smem, int r,
-                                                 uint32_t (&out)[64]) {
+  // thread r (= TMEM lane = weight row of the tile), k-half h: 32 packed bytes + up to 2 (s,z) pairs -> 32 bf16x2
+  // (out[c] = k pair 64h + 2c, 64h + 2c + 1).  The row's 64 bytes are four 16-byte lane words (tinygemm word
+  // wd = k 32wd..32wd+31 sits at byte 4wd of each); half h needs words 2h, 2h+1 = the 8 bytes at +8h of each.
+  __device__ static __forceinline__ void dequant_half(const tsg::Params& p, uint32_t w_smem, uint32_t aux_smem, int r,
+                                                      int h, uint32_t (&out)[32]) {
     const uint32_t row_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u;
     const int gshift = p.group_size == 32 ? 0 : (p.group_size == 64 ? 1 : 2);  // word -> group
-    uint4 v[4];
+    uint2 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t off = row_off + i * 16;
-      v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 7) << 4)));  // undo the TMA 128B swizzle
+      v[i] = tsg::lds64(w_smem + (off ^ (((off >> 7) & 7) << 4)) + 8 * h);  // undo the TMA 128B swizzle
     }
-    uint32_t sz[4];  // (s,z) of the group each 32-k word belongs to
+    uint32_t sz[2];  // (s,z) of the group each 32-k word belongs to
 #pragma unroll
-    for (int wd = 0; wd < 4; ++wd) sz[wd] = tsg::lds32(aux_smem + r * 4 + (wd >> gshift) * 512);
+    for (int w2 = 0; w2 < 2; ++w2) sz[w2] = tsg::lds32(aux_smem + r * 4 + ((2 * h + w2) >> gshift) * 512);
 #pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
-      const uint32_t s_bits = __byte_perm(sz[wd], sz[wd], 0x1010);
-      const uint32_t z_bits = __byte_perm(sz[wd], sz[wd], 0x3232);
+    for (int w2 = 0; w2 < 2; ++w2) {
+      const uint32_t s_bits = __byte_perm(sz[w2], sz[w2], 0x1010);
+      const uint32_t z_bits = __byte_perm(sz[w2], sz[w2], 0x3232);
       const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
       const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&z_bits);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t word = (wd == 0) ? v[i].x : (wd == 1) ? v[i].y : (wd == 2) ? v[i].z : v[i].w;
+        const uint32_t word = (w2 == 0) ? v[i].x : v[i].y;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t m = ((word >> (4 * e)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 of 128+q
-          out[16 * wd + i + 4 * e] = deq_pair(m, s2, z2);                         // k pair (32wd+2i+8e, +1)
+          out[16 * w2 + i + 4 * e] = deq_pair(m, s2, z2);                         // k pair (64h+32w2+2i+8e, +1)
         }
       }
     }
@@ -133,11 +135,11 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
 }
 
 
-template <int N_MMA>
+template <int N_MMA, int DBUF = 2>
 static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
                      const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes,
                      cudaStream_t stream) {
-  using C = tsg::Cfg<N_MMA>;
+  using C = tsg::Cfg<N_MMA, DBUF>;
   const int KT = K / 128;
   CUtensorMap tm_w, tm_sz, tm_x;
   {
@@ -175,13 +177,13 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
   const long long units = (long long)p.n_tiles * p.m_blocks * KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  int grid = sm_count();
+  int grid = sm_count() * (N_MMA <= 64 ? ts_ctas_per_sm() : 1);
   if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)
     return fail(AO_ERR_WORKSPACE, "int4 linear: workspace too small (%zu < %zu)", ws_bytes, need);
-  auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true>
-                                           : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false>;
+  auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true, DBUF>
+                                           : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false, DBUF>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[p.timeline ? 1 : 0]) {
     AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -223,9 +225,14 @@ extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const 
   if (M <= 16)
     return int4k::launch_tc<16>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
-  if (M <= 32)
+  if (M <= 32) {
+    // bring-up switch: AO_B200_TS_FLAGS & 16 = single-buffered accumulators (3 A stages instead of 2)
+    if (ts_flags() & 16)
+      return int4k::launch_tc<32, 1>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+                                     workspace_bytes, st);
     return int4k::launch_tc<32>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
+  }
   if (M <= 64)
     return int4k::launch_tc<64>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);

@@ -39,30 +39,30 @@ struct Nvfp4Fmt {
                  "l"(src), "r"(1024), "r"(smem_u32(bar))
                  : "memory");
   }
-  __device__ static __forceinline__ void dequant(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
-                                                 uint32_t (&out)[64]) {
-    uint4 v[4];
+  // k-half h of row r: bytes 32h..32h+31 (k 64h..64h+63) and the four block scales of blocked tile h
+  __device__ static __forceinline__ void dequant_half(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
+                                                      int h, uint32_t (&out)[32]) {
+    uint4 v[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t off = (uint32_t)r * 64u + i * 16;
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t off = (uint32_t)r * 64u + (2 * h + i) * 16;
       v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 3) << 4)));  // undo the TMA 64B swizzle
     }
-    // 8 scale bytes of this row: blocked tile j holds k-blocks 4j..4j+3
     const uint32_t sc_off = (uint32_t)(r & 31) * 16u + (uint32_t)(r >> 5) * 4u;
-    const uint32_t sc[2] = {tsg::lds32(aux_smem + sc_off), tsg::lds32(aux_smem + 512 + sc_off)};
+    const uint32_t sc = tsg::lds32(aux_smem + 512 * h + sc_off);
     const uint32_t two120 = 0x7B807B80u;  // bf16x2 of 2^120
     const __nv_bfloat162 c120 = *reinterpret_cast<const __nv_bfloat162*>(&two120);
 #pragma unroll
-    for (int w = 0; w < 16; ++w) {  // word w = bytes 4w..4w+3 = k 8w..8w+7; scale block = w/2
+    for (int w = 0; w < 8; ++w) {  // word w = bytes 4w..4w+3 of the half = k 8w..8w+7; scale block = w/2
       const uint32_t word = (w & 3) == 0 ? v[w >> 2].x : (w & 3) == 1 ? v[w >> 2].y : (w & 3) == 2 ? v[w >> 2].z : v[w >> 2].w;
-      const uint32_t sb = (sc[w >> 3] >> (8 * ((w >> 1) & 3))) & 0xFFu;
+      const uint32_t sb = (sc >> (8 * (w >> 1))) & 0xFFu;
       const uint32_t s_bits = ((sb << 4) + 0x3F00u) * 0x00010001u;  // bf16x2 of scale * 2^6
       const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t t = word >> (8 * j);
-        const uint32_t h = (t & 0xFu) | ((t << 12) & 0xF0000u);       // even k -> low half, odd k -> high half
-        const uint32_t bits = (h * 0x1040u) & 0x81C081C0u;            // sign | e1 e0 m at bf16 bits 15 | 8:6
+        const uint32_t hh = (t & 0xFu) | ((t << 12) & 0xF0000u);      // even k -> low half, odd k -> high half
+        const uint32_t bits = (hh * 0x1040u) & 0x81C081C0u;           // sign | e1 e0 m at bf16 bits 15 | 8:6
         __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&bits);
         x = __hmul2(x, c120);
         x = __hmul2(x, s2);
@@ -109,7 +109,7 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  int grid = sm_count();
+  int grid = sm_count() * (N_MMA <= 64 ? ts_ctas_per_sm() : 1);
   if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)

@@ -7,14 +7,25 @@
 //   * swap-AB: 128 weight rows = UMMA M, tokens = UMMA N (16..128), fp32 accumulator in TMEM
 //   * persistent, one CTA per SM; the (n-tile, 128-k chunk) units of the whole GEMM are split EVENLY
 //     over the CTAs ("stream-K"), so every SM issues the same number of MMAs whatever N/K are
-//   * 16 warps in four warpgroups with register redistribution (setmaxnreg):
-//       WG0, WG1 (warps 0-7, 96 regs): dequant, alternating chunks: ld.shared (conflict-free through the
-//                  TMA swizzle) -> unpack/scale in bf16x2 -> tcgen05.st of the bf16 A operand into TMEM
-//       WG2 (warps 8-11, 32 regs)    : epilogue: tcgen05.ld of a finished accumulator (double-buffered,
+//   * 16 warps in four warpgroups, 64 registers per thread:
+//       WG0, WG1 (warps 0-7): dequant, alternating chunks: ld.shared (conflict-free through the TMA
+//                  swizzle) -> unpack/scale in bf16x2, one 64-k half row (32 registers) at a time ->
+//                  tcgen05.st of the bf16 A operand into TMEM
+//       WG2 (warps 8-11)             : epilogue: tcgen05.ld of a finished accumulator (double-buffered,
 //                  overlaps the next tile's MMAs), split-tile fix-up through an fp32 workspace, bias, store
-//       WG3 (warp 12 TMA producer, warp 13 MMA issuer, warps 14-15 idle; 32 regs)
-//     64 registers/thread at launch + 256 TMEM columns + ~105 KB smem => two CTAs fit on an SM, so the next
-//     linear's CTA (PDL) is already resident and prefetching weights while this one drains
+//       WG3 (warp 12 weight TMA producer, warps 13 and 15 MMA issuers, warp 14 activation TMA producer)
+//     One thread can issue a tcgen05.mma only every ~58-70 cycles, and every other memory-pipe operation of
+//     that thread (mbarrier wait, commit) costs it another 100-300 cycles (scripts/mma_microbench*.cu), so the
+//     issuer's loop is stripped to ONE wait and ONE commit per chunk: the activation slot of a chunk shares the
+//     index and the barriers of the chunk's TMEM A stage (afull[t] = 4 dequant arrivals + the activation
+//     tile's transaction bytes; one tcgen05.commit on aempty[t] frees both), and for UMMA N <= 32 there are TWO
+//     issuers (issue rate scales linearly with issuing warps): even chunks go to issuer 0, odd chunks to
+//     issuer 1, each into its own TMEM accumulator; the epilogue adds the two in a fixed order, so results
+//     stay bit-reproducible.
+//     64 registers/thread at launch + 256 TMEM columns + ~105 KB smem => two CTAs fit on an SM.  The grid is
+//     two CTAs per SM: per-thread costs (MMA issue, TMA issue, barrier round trips) are what bound one CTA,
+//     so two independent CTAs per SM double the streaming rate, and a finishing CTA's slot is refilled by the
+//     next linear's CTA (PDL) which prefetches weights while its neighbour drains
 //   * tiles split across CTAs are reduced deterministically: every CTA writes its partial, bumps the
 //     tile's unit counter, and whoever completes the count sums the partials in CTA order
 //   * PDL: griddepcontrol.launch_dependents at start; weights are prefetched before
@@ -33,21 +44,31 @@ constexpr int KCHUNK = 128;
 constexpr int W_BYTES = ROWS * KCHUNK / 2;  // 8 KiB of 4-bit weights per chunk
 constexpr int AUX_BYTES = 2048;             // scales per chunk (<= 2 KiB), 1 KiB aligned slot
 constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage (128 k / 2)
-constexpr int DEQ_WARPS = 8, EPI_WARP0 = 8, TMA_WARP = 12, MMA_WARP = 13;
+constexpr int DEQ_WARPS = 8, EPI_WARP0 = 8, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14, MMA_WARP1 = 15;
+constexpr int WSTAGE_BYTES = W_BYTES + AUX_BYTES;  // one weight stage: packed nibbles + scales
 constexpr int NUM_THREADS = 16 * 32;
 constexpr int REGS_DEQ = 96, REGS_OTHER = 32;
 
-template <int N_MMA>
+// DBUF = accumulator buffers per issuer (2: the epilogue of a tile overlaps the next tile's MMAs)
+template <int N_MMA, int DBUF = 2>
 struct Cfg {
-  static constexpr int X_BYTES = 2 * N_MMA * 128;
-  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES + AUX_BYTES;
-  static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 172 * 1024;
-  static constexpr int STAGES = BUDGET / STAGE_BYTES;
+  static constexpr int X_BYTES = 2 * N_MMA * 128;   // activation tile of one chunk (two 64-k swizzle atoms)
+  // MMA issuer warps, one private accumulator set each.  One issuer reaches the tensor pipe's own limit (20 cycles
+  // per M128 N16 K16 MMA) once its operands live in uniform registers; the two-issuer path (NI = 2, even / odd
+  // chunks, accumulators added by the epilogue in a fixed order) is kept for experiments.
+  static constexpr int NI = 1;
   static constexpr int TMEM_COLS = N_MMA <= 64 ? 256 : 512;
-  static constexpr int D_COL0 = 0, D_COL1 = N_MMA;
-  static constexpr int A_COL0 = N_MMA <= 32 ? 64 : 2 * N_MMA;
-  static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int D_COLS = NI * DBUF * N_MMA;
+  static constexpr int A_COL0 = D_COLS <= 64 ? 64 : (D_COLS <= 128 ? 128 : 256);
+  static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4; also the depth of the activation ring
+  static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 172 * 1024;
+  // weight stages (8, 8, 6 or 4): even, so that a stage is always consumed by the same dequant warpgroup and
+  // every waiter of a barrier observes each of its phases
+  static constexpr int STAGES = ((BUDGET - A_STAGES * X_BYTES) / WSTAGE_BYTES) & ~1;
+  static constexpr int X_OFF = STAGES * WSTAGE_BYTES;
+  static constexpr int BAR_OFF = X_OFF + A_STAGES * X_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)BAR_OFF + 1024 + 1024;
+  __host__ __device__ static constexpr int d_col(int issuer, int buf) { return (issuer * DBUF + buf) * N_MMA; }
 };
 
 struct Params {
@@ -123,41 +144,48 @@ __device__ __forceinline__ int cta_of_unit(int u, long long U, int G) {
 // Fmt policy:
 //   static void issue_w(tm_w, tm_aux, p, w smem dst, aux smem dst, full barrier, n_tile, kc, policy)  (one thread)
 //   static uint32_t w_tx_bytes(p)
-//   static void dequant(p, w smem, aux smem, row r, out[64])      (128 threads; out[c] = bf16x2 of k = 2c, 2c+1)
+//   static void dequant_half(p, w smem, aux smem, row r, half h, out[32])   (128 threads; out[c] = bf16x2 of
+//                                                                            k = 64h + 2c, 64h + 2c + 1)
 // TL = true compiles the per-CTA phase-timestamp instrumentation in (bring-up builds only).
-template <class Fmt, int N_MMA, bool TL = false>
+template <class Fmt, int N_MMA, bool TL = false, int DBUF = 2>
 __global__ void __launch_bounds__(NUM_THREADS, (N_MMA <= 64 ? 2 : 1))
 ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_aux,
                const __grid_constant__ CUtensorMap tm_x, const Params p) {
-  using C = Cfg<N_MMA>;
+  using C = Cfg<N_MMA, DBUF>;
+  constexpr int NI = C::NI;
   constexpr int S = C::STAGES;
   constexpr int T = C::A_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * C::STAGE_BYTES);
-  uint64_t* wfull = bars;             // [S]
-  uint64_t* xfull = wfull + S;        // [S]
-  uint64_t* sempty = xfull + S;       // [S]   4 dequant warps (the chunk's warpgroup) + MMA commit
-  uint64_t* afull = sempty + S;       // [T]   4 dequant warps
-  uint64_t* aempty = afull + T;       // [T]   MMA commit
-  uint64_t* dfull = aempty + T;       // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* wfull = bars;             // [S]   weight TMA transaction
+  uint64_t* sempty = wfull + S;       // [S]   4 dequant warps (the chunk's warpgroup) have the weights in registers
+  // A-stage barriers come in PAIRS per stage (use k = chunk / T of the stage goes to barrier k & 1, phase
+  // k >> 1): with T odd consecutive uses of a stage belong to different warpgroups / issuers, and a parity
+  // wait by a party that skips every other phase would alias; per pair every waiter sees every phase.
+  uint64_t* afull = sempty + S;       // [T][2] 4 dequant warps (A stage stored) + activation TMA (arrive.expect_tx)
+  uint64_t* aempty = afull + 2 * T;   // [T][2] MMA commit: A stage and activation slot both free
+  uint64_t* dfull = aempty + 2 * T;   // [2]   one arrival per issuer and accumulator segment
   uint64_t* dempty = dfull + 2;       // [2]   4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   uint32_t* flag_slot = tmem_slot + 1;
 
-  // role (virtual) warp id; shifting by two warpgroups keeps the TMEM lane quarter (warp & 3) intact
-  const int warp = ((threadIdx.x >> 5) + ((p.flags & 1) ? 8 : 0)) & 15, lane = threadIdx.x & 31;
-  const bool nap = (p.flags & 2) != 0;
+  // The warp index goes through a shuffle so that the compiler knows it is warp-uniform: the single-thread
+  // roles below run as warp-uniform loops with only the tcgen05 / TMA / mbarrier instruction itself under
+  // elect.sync.  With the whole loop under `lane == 0` instead, ptxas treats every operand as divergent and
+  // wraps each UTCHMMA / UTMALDG in an elect-broadcast "waterfall" loop (52 instead of 20 cycles per MMA,
+  // scripts/mma_microbench7.cu).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
   const long long t_entry = TL ? clock64() : 0;
   auto stamp = [&](int e) {
-    if (TL && p.timeline) p.timeline[(size_t)b * 8 + e] = (unsigned long long)(clock64() - t_entry);
+    if (TL && p.timeline && b < 148) p.timeline[(size_t)b * 8 + e] = (unsigned long long)(clock64() - t_entry);
   };
   // fine-grained stamps of units 8..11 of CTA 0 (chain latencies), stored after the per-CTA table
   auto stamp2 = [&](int i, int e) {
     if (TL && p.timeline && b == 0 && i >= 8 && i < 12) p.timeline[148 * 8 + (i - 8) * 8 + e] = (unsigned long long)(clock64() - t_entry);
   };
-  if (TL && p.timeline && threadIdx.x == 0) {
+  if (TL && p.timeline && threadIdx.x == 0 && b < 148) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.timeline[(size_t)b * 8] = gt;
@@ -169,15 +197,14 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&wfull[i], 1);
-      mbar_init(&xfull[i], 1);
-      mbar_init(&sempty[i], 5);
+      mbar_init(&sempty[i], 4);
     }
-    for (int i = 0; i < T; ++i) {
-      mbar_init(&afull[i], 4);
+    for (int i = 0; i < 2 * T; ++i) {
+      mbar_init(&afull[i], 5);
       mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&dfull[i], 1);
+      mbar_init(&dfull[i], NI);
       mbar_init(&dempty[i], 4);
     }
     fence_barrier_init();
@@ -185,13 +212,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_aux);
-    tma_prefetch_desc(&tm_x);
   }
+  if (warp == XTMA_WARP && lane == 0) tma_prefetch_desc(&tm_x);
   if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_launch_dependents();
   if (threadIdx.x == 0) stamp(1);
 
@@ -201,99 +228,125 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 
   if (warp < DEQ_WARPS) {
     // ------------------------------------------------------------ dequant warpgroups (0: even, 1: odd chunks)
-    reg_inc<REGS_DEQ>();
     const int wg = warp >> 2, q4 = warp & 3;
     const int r = q4 * 32 + lane;  // weight row of the tile == TMEM lane
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     for (int i = wg; i < nunits; i += 2) {
-      const int s = i % S, t = i % T;
-      const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+      const int s = i % S, t = i % T, k = i / T;
+      const uint32_t st = smem_u32(smem + (size_t)s * WSTAGE_BYTES);
+      const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
       mbar_wait(&wfull[s], (i / S) & 1);
       if (i == 0 && warp == 0 && lane == 0) stamp(3);
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 0);
-      uint32_t out[64];
-      Fmt::dequant(p, st, st + W_BYTES + C::X_BYTES, r, out);
+      // the row in two 64-k halves (32 registers of output each): half 0 is computed before the A stage is
+      // known to be free, so the wait overlaps its arithmetic
+      uint32_t out[32];
+      Fmt::dequant_half(p, st, st + W_BYTES, r, 0, out);
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 1);
-      mbar_wait(&aempty[t], ((i / T) & 1) ^ 1);
+      if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);  // MMAs of chunk i - T are done
       tc_fence_after();
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 2);
-      const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
       tmem_st_x32(a_t, out);
-      tmem_st_x32(a_t + 32, out + 32);
+      tc_wait_st();   // the registers are reused by the second half
+      Fmt::dequant_half(p, st, st + W_BYTES, r, 1, out);
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
+      tmem_st_x32(a_t + 32, out);
       tc_wait_st();
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 3);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&afull[t]);
-        mbar_arrive(&sempty[s]);
-      }
+      if (elect_one()) mbar_arrive(&afull[t * 2 + (k & 1)]);
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 4);
     }
   } else if (warp >= TMA_WARP) {
-    reg_dec<REGS_OTHER>();
     if (warp == TMA_WARP) {
-      if (lane == 0 && nunits > 0) {
-        const uint64_t pol_w = policy_evict_first();
-        const uint64_t pol_x = policy_evict_last();
-        auto issue_w = [&](int i) {
-          const int s = i % S, tile = tile_of(i);
-          uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
-          mbar_expect_tx(&wfull[s], Fmt::w_tx_bytes(p));
-          Fmt::issue_w(&tm_w, &tm_aux, p, st, st + W_BYTES + C::X_BYTES, &wfull[s], tile % p.n_tiles, kc_of(i), pol_w);
-        };
-        auto issue_x = [&](int i) {
-          const int s = i % S, tile = tile_of(i);
-          uint8_t* st = smem + (size_t)s * C::STAGE_BYTES + W_BYTES;
-          const int m0 = (tile / p.n_tiles) * N_MMA, k0 = kc_of(i) * KCHUNK;
-          mbar_expect_tx(&xfull[s], C::X_BYTES);
-          tma_load_2d(st, &tm_x, &xfull[s], k0, m0, pol_x);
-          tma_load_2d(st + N_MMA * 128, &tm_x, &xfull[s], k0 + 64, m0, pol_x);
-        };
-        const int pre = nunits < S ? nunits : S;
-        for (int i = 0; i < pre; ++i) issue_w(i);  // weights never depend on the previous kernel
-        pdl_wait();
-        stamp(2);
-        for (int i = 0; i < pre; ++i) issue_x(i);
-        for (int i = S; i < nunits; ++i) {
-          while (!mbar_try_wait(&sempty[i % S], ((i / S) & 1) ^ 1)) { if (nap) __nanosleep(64); }
-          issue_w(i);
-          issue_x(i);
-        }
-      }
-    } else if (warp == MMA_WARP) {
-      constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);
-      int seg = 0;  // accumulator segment counter (one per tile touched)
+      // ---------------------------------------------------------- weight producer.  Weights never depend on the
+      // previous kernel: no griddepcontrol.wait on this path.
+      const uint64_t pol_w = policy_evict_first();
+      int s = 0, sph = 0, kc = kc_of(0), n_tile = tile_of(0) % p.n_tiles;
       for (int i = 0; i < nunits; ++i) {
-        const int s = i % S, t = i % T;
-        const bool first = (i == 0) || (kc_of(i) == 0);
-        const bool last = (i == nunits - 1) || (kc_of(i) == p.KT - 1);
-        const int buf = seg & 1;
-        if (first) {
-          mbar_wait(&dempty[buf], ((seg >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-        }
-        while (!mbar_try_wait(&xfull[s], (i / S) & 1)) { if (nap) __nanosleep(32); }
-        while (!mbar_try_wait(&afull[t], (i / T) & 1)) { if (nap) __nanosleep(32); }
-        tc_fence_after();
-        if (lane == 0) {
-          if (i == 0) stamp(4);
-          stamp2(i, 5);
-          const uint32_t xb = smem_u32(smem + (size_t)s * C::STAGE_BYTES + W_BYTES);
-          mma_chunk_ts_f16(tmem_base + (buf ? C::D_COL1 : C::D_COL0), tmem_base + C::A_COL0 + t * A_COLS,
-                           umma_desc_k_sw128(xb), umma_desc_k_sw128(xb + N_MMA * 128), idesc, first ? 0u : 1u);
-          tc_commit(&aempty[t]);
-          tc_commit(&sempty[s]);
-          if (last) tc_commit(&dfull[buf]);
-          stamp2(i, 6);
-          if (i == nunits - 1) stamp(5);
+        if (i >= S) mbar_wait(&sempty[s], sph ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + (size_t)s * WSTAGE_BYTES;
+          mbar_expect_tx(&wfull[s], Fmt::w_tx_bytes(p));
+          Fmt::issue_w(&tm_w, &tm_aux, p, st, st + W_BYTES, &wfull[s], n_tile, kc, pol_w);
         }
         __syncwarp();
-        if (last) ++seg;
+        if (++s == S) { s = 0; sph ^= 1; }
+        if (++kc == p.KT) { kc = 0; if (++n_tile == p.n_tiles) n_tile = 0; }
+      }
+    } else if (warp == XTMA_WARP) {
+      // ---------------------------------------------------------- activation producer
+      if (nunits > 0) {
+        const uint64_t pol_x = policy_evict_last();
+        pdl_wait();   // activations are the previous kernel's output
+        if (lane == 0) stamp(2);
+        int t = 0, k = 0, kc = kc_of(0), tile = tile_of(0);
+        for (int i = 0; i < nunits; ++i) {
+          uint64_t* full = &afull[t * 2 + (k & 1)];
+          if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);
+          if (elect_one()) {
+            uint8_t* xs = smem + C::X_OFF + (size_t)t * C::X_BYTES;
+            const int m0 = (tile / p.n_tiles) * N_MMA, k0 = kc * KCHUNK;
+            mbar_expect_tx(full, C::X_BYTES);
+            tma_load_2d(xs, &tm_x, full, k0, m0, pol_x);
+            tma_load_2d(xs + N_MMA * 128, &tm_x, full, k0 + 64, m0, pol_x);
+          }
+          __syncwarp();
+          if (++t == T) { t = 0; ++k; }
+          if (++kc == p.KT) { kc = 0; ++tile; }
+        }
+      }
+    } else if (warp == MMA_WARP || (NI == 2 && warp == MMA_WARP1)) {
+      // ---------------------------------------------------------- MMA issuers: chunk c belongs to issuer c % NI
+      constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);
+      const int j = (warp == MMA_WARP) ? 0 : 1;
+      const uint32_t x0 = smem_u32(smem + C::X_OFF);
+      int seg = 0, i = 0, kc0 = kc_of(0);
+      while (i < nunits) {
+        int cnt = p.KT - kc0;   // units of this accumulator segment
+        if (cnt > nunits - i) cnt = nunits - i;
+        const int buf = seg % DBUF, ph = (seg / DBUF) & 1;
+        // every issuer passes through every segment's dempty/dfull phase, chunks or not (keeps the phases in step)
+        mbar_wait(&dempty[buf], ph ^ 1);
+        const uint32_t d_t = tmem_base + C::d_col(j, buf);
+        int c = i + ((j - i) & (NI - 1));
+        int t = c % T, k = c / T;
+        uint32_t acc = 0;   // first MMA of the segment overwrites the accumulator
+        for (; c < i + cnt; c += NI) {
+          mbar_wait(&afull[t * 2 + (k & 1)], (k >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (c == 0) stamp(4);
+            stamp2(c, 5);
+            const uint32_t xb = x0 + t * C::X_BYTES;
+            const uint32_t a_t = tmem_base + C::A_COL0 + t * A_COLS;
+            const uint64_t b_lo = umma_desc_k_sw128(xb), b_hi = umma_desc_k_sw128(xb + N_MMA * 128);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              mma_ts_f16(d_t, a_t + kk * 8, (kk < 4 ? b_lo : b_hi) + (uint64_t)((kk & 3) * 2), idesc, (kk == 0) ? acc : 1u);
+            tc_commit(&aempty[t * 2 + (k & 1)]);
+            stamp2(c, 6);
+            if (c == nunits - 1) stamp(5);
+          }
+          __syncwarp();
+          acc = 1u;
+          t += NI;
+          if (t >= T) { t -= T; ++k; }
+        }
+        if (elect_one()) {
+          if (acc) tc_commit(&dfull[buf]);   // all of this issuer's MMAs of the segment have completed
+          else mbar_arrive(&dfull[buf]);     // no chunk of this segment was ours
+        }
+        __syncwarp();
+        i += cnt;
+        ++seg;
+        kc0 = 0;
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (8..11)
-    reg_dec<REGS_OTHER>();
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -305,31 +358,50 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       const int kc_first = kc_of(i);
       int cnt = p.KT - kc_first;
       if (cnt > nunits - i) cnt = nunits - i;
-      const int buf = seg & 1;
-      while (!mbar_try_wait(&dfull[buf], (seg >> 1) & 1)) __nanosleep(200);  // long wait: do not steal issue slots
+      const int buf = seg % DBUF;
+      while (!mbar_try_wait(&dfull[buf], (seg / DBUF) & 1)) __nanosleep(200);  // long wait: do not steal issue slots
       tc_fence_after();
       if (i + cnt >= nunits && (warp == EPI_WARP0 && lane == 0)) stamp(6);
       const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
-      const uint32_t d_t = lane_taddr + (buf ? C::D_COL1 : C::D_COL0);
+      // which issuers contributed to this segment (chunk c -> issuer c % NI); their accumulators add in fixed order
+      const bool has0 = (NI == 1) || cnt >= 2 || (i & 1) == 0;
+      const bool has1 = (NI == 2) && (cnt >= 2 || (i & 1) == 1);
+      const uint32_t d_t0 = lane_taddr + C::d_col(0, buf);
+      const uint32_t d_t1 = lane_taddr + C::d_col(NI - 1, buf);
+      auto load8 = [&](int j8, float* v) {
+        uint32_t ra[8], rb[8];
+        if (has0)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(ra[0]), "=r"(ra[1]), "=r"(ra[2]), "=r"(ra[3]), "=r"(ra[4]), "=r"(ra[5]), "=r"(ra[6]), "=r"(ra[7])
+                       : "r"(d_t0 + j8)
+                       : "memory");
+        if (has1)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(rb[0]), "=r"(rb[1]), "=r"(rb[2]), "=r"(rb[3]), "=r"(rb[4]), "=r"(rb[5]), "=r"(rb[6]), "=r"(rb[7])
+                       : "r"(d_t1 + j8)
+                       : "memory");
+        tc_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a = has0 ? __uint_as_float(ra[q]) : 0.f;
+          v[q] = has1 ? (has0 ? a + __uint_as_float(rb[q]) : __uint_as_float(rb[q])) : a;
+        }
+      };
       const float bias = (p.bias && n < p.N_out) ? __bfloat162float(p.bias[n]) : 0.f;
       const float osc = p.out_scale ? *p.out_scale : 1.f;
       if (cnt == p.KT) {
         // the whole K range of this tile was ours: straight to the output
 #pragma unroll 1
         for (int j = 0; j < N_MMA; j += 8) {
-          uint32_t rr[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
-                       : "r"(d_t + j)
-                       : "memory");
-          tc_wait_ld();
+          float rr[8];
+          load8(j, rr);
           if (n < p.N_out) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int m = m0 + j + q;
               if (m < p.M) {
-                float v = __uint_as_float(rr[q]);
+                float v = rr[q];
                 if (p.row_scale) v *= p.row_scale[m];
                 p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(v * osc + bias);
               }
@@ -345,15 +417,11 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         float* slot = p.ws_partial + ((size_t)b * 2 + which) * (N_MMA * ROWS);
 #pragma unroll 1
         for (int j = 0; j < N_MMA; j += 8) {
-          uint32_t rr[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
-                       : "r"(d_t + j)
-                       : "memory");
-          tc_wait_ld();
+          float rr[8];
+          load8(j, rr);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS + r], __uint_as_float(rr[q]));
+            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS + r], rr[q]);
         }
         tc_fence_before();
         __syncwarp();
@@ -407,9 +475,11 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     if ((warp == EPI_WARP0 && lane == 0)) stamp(7);
   }
 
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
