@@ -93,8 +93,8 @@ int ts_ctas_per_sm() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("AO_B200_TS_CTAS_PER_SM");
-    v = e ? atoi(e) : 2;
-    if (v < 1 || v > 2) v = 2;
+    v = e ? atoi(e) : 0;   // 0 = choose per problem size
+    if (v < 0 || v > 2) v = 0;
   }
   return v;
 }

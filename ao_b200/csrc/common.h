@@ -68,7 +68,7 @@ bool pdl_enabled();
 // AO_B200_TIMELINE=1: kernels record per-CTA phase timestamps at workspace + 48 KiB (bring-up only).
 bool timeline_enabled();
 int ts_flags();  // AO_B200_TS_FLAGS bring-up switches for ts_gemm.cuh
-int ts_ctas_per_sm();  // AO_B200_TS_CTAS_PER_SM (1 or 2, default 2): grid size of ts_gemm.cuh in CTAs per SM
+int ts_ctas_per_sm();  // AO_B200_TS_CTAS_PER_SM (1 or 2; default 0 = by problem size): grid of ts_gemm.cuh in CTAs per SM
 int sm_count();
 
 }  // namespace ao

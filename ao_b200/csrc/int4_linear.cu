@@ -55,6 +55,8 @@ struct Int4Fmt {
                                                       int h, uint32_t (&out)[32]) {
     const uint32_t row_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u;
     const int gshift = p.group_size == 32 ? 0 : (p.group_size == 64 ? 1 : 2);  // word -> group
+    uint32_t magic = 0x43004300u;
+    asm volatile("" : "+r"(magic));  // keep it in a register
     uint2 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -75,7 +77,10 @@ struct Int4Fmt {
         const uint32_t word = (w2 == 0) ? v[i].x : v[i].y;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t m = ((word >> (4 * e)) & 0x000F000Fu) | 0x43004300u;  // bf16x2 of 128+q
+          // bf16x2 of 128+q = ((word >> 4e) & 0x000F000F) | 0x43004300 as ONE lop3 (the integer pipe is what
+          // bounds this kernel; C source compiles to two LOP3 because both constants want the immediate slot)
+          uint32_t m;
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(m) : "r"(word >> (4 * e)), "r"(0x000F000Fu), "r"(magic));
           out[16 * w2 + i + 4 * e] = deq_pair(m, s2, z2);                         // k pair (64h+32w2+2i+8e, +1)
         }
       }
@@ -174,10 +179,18 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   p.m_blocks = ceil_div(M, N_MMA);
   p.KT = KT;
   p.flags = ts_flags();
-  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
+  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 8 stamps + 4 x 8 fine stamps
+  static unsigned tl_launch = 0;
+  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024 +
+                                                                         (size_t)(tl_launch++ & 1) * (100 * 8 + 32) * 8)
+                                  : nullptr;
   const long long units = (long long)p.n_tiles * p.m_blocks * KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  int grid = sm_count() * (N_MMA <= 64 ? ts_ctas_per_sm() : 1);
+  // two CTAs per SM (twice the warps hiding the per-chunk latencies) when a CTA would otherwise get fewer than
+  // 16 chunks; with longer ranges one CTA per SM leaves room for the next linear's CTA to become resident and
+  // prefetch its weights under this one (PDL), which is worth more
+  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : (units < 16LL * sm_count() ? 2 : 1);
+  int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
   if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)

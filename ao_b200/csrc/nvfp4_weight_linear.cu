@@ -109,7 +109,11 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  int grid = sm_count() * (N_MMA <= 64 ? ts_ctas_per_sm() : 1);
+  // two CTAs per SM (twice the warps hiding the per-chunk latencies) when a CTA would otherwise get fewer than
+  // 16 chunks; with longer ranges one CTA per SM leaves room for the next linear's CTA to become resident and
+  // prefetch its weights under this one (PDL), which is worth more
+  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : (units < 16LL * sm_count() ? 2 : 1);
+  int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
   if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)

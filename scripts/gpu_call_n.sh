@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== chain probe"; timeout 60 python -u scripts/gpu_hang_probe.py 14336 4096 1 2>&1 | tail -2; timeout 60 python -u scripts/gpu_hang_probe.py 4096 14336 32 2>&1 | tail -2
+timeout 200 python -u scripts/gpu_probe_int4.py --stages diag,tc 2>&1 | grep -E "RESULT|FAIL|rror|identical|== stage|sqnr\(ours,fp32\)= *(-|nan|[0-3][0-9]\.)" | tail -8
+for c in 2 1; do
+  echo "=== AO_B200_TS_CTAS_PER_SM=$c"
+  AO_B200_TS_CTAS_PER_SM=$c timeout 150 python -u scripts/gpu_prof_int4.py sweep 2>&1 | tail -13
+done
+for c in 1 2; do
+  echo "=== timeline CTAS_PER_SM=$c"; AO_B200_TS_CTAS_PER_SM=$c timeout 100 python scripts/gpu_timeline.py 1,32 2>&1 | tail -10
+done

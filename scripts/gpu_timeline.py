@@ -1,6 +1,7 @@
-"""Per-CTA phase timeline of the TS-mode GEMM (AO_B200_TIMELINE=1).  Prints, per shape, the median/max over
-CTAs of each phase (cycles from kernel entry): 1 prologue done, 2 pdl_wait returned, 3 first weights landed,
-4 first MMA issued, 5 last MMA issued, 6 last accumulator ready, 7 epilogue done; plus the spread of entry times."""
+"""Absolute (globaltimer) phase timeline of the TS-mode GEMM over a chain of launches (AO_B200_TIMELINE=1).
+Per CTA stamps: 0 entry, 1 prologue done, 2 pdl_wait returned, 3 first weights landed, 4 first MMA issued,
+5 last MMA issued, 6 last accumulator ready, 7 epilogue done.  Two timeline slots alternate between launches, so the
+last two kernels of a chain can be laid on one time axis: how much of kernel k+1 overlaps kernel k."""
 import os
 import sys
 
@@ -12,6 +13,7 @@ sys.path.insert(0, ROOT)
 torch.ops.load_library(os.path.join(ROOT, "ao_b200", "lib", "ao_b200_torch.so"))
 ops = torch.ops.ao_b200
 g = 32
+SLOT = (100 * 8 + 32) * 8
 
 
 def mk(N, K):
@@ -20,43 +22,35 @@ def mk(N, K):
     return qd, sz
 
 
-def read_tl(x, ncta):
-    ws = ops.debug_workspace(x)
-    tl = ws[48 * 1024: 48 * 1024 + 148 * 64].view(torch.int64).reshape(148, 8)[:ncta].cpu()
-    return tl
+def slot(ws, i):
+    return ws[48 * 1024 + i * SLOT: 48 * 1024 + i * SLOT + 100 * 64].view(torch.int64).reshape(100, 8).cpu()
 
 
 Ms = (1, 32) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split(','))
+shapes = [(14336, 4096)] if len(sys.argv) < 3 else [tuple(int(v) for v in sys.argv[2].split('x'))]
+names = ["entry", "prologue", "pdl_wait", "w_landed", "mma_first", "mma_last", "acc_ready", "done"]
 for M in Ms:
-    for (N, K) in [(14336, 4096)]:
+    for (N, K) in shapes:
         x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-        wa, wb = mk(N, K), mk(N, K)
-        for back_to_back in (False, True):
-            for _ in range(2):
-                ops.int4_tilepacked_linear(x, wa[0], g, wa[1], None, N, 1)
-            torch.cuda.synchronize()
-            ws = ops.debug_workspace(x)
-            ws[48 * 1024: 48 * 1024 + 148 * 64].zero_()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if back_to_back:
-                ops.int4_tilepacked_linear(x, wa[0], g, wa[1], None, N, 1)
-            ops.int4_tilepacked_linear(x, wb[0], g, wb[1], None, N, 1)
-            e1.record()
-            torch.cuda.synchronize()
-            tl = read_tl(x, 148)
-            used = (tl[:, 7] > 0)
-            tl = tl[used]
-            gt = tl[:, 0]
-            ph = tl[:, 1:].float()
-            med = ph.median(dim=0).values.tolist()
-            mx = ph.max(dim=0).values.tolist()
-            ws2 = ops.debug_workspace(x)
-            fine = ws2[48 * 1024 + 148 * 64: 48 * 1024 + 148 * 64 + 4 * 64].view(torch.int64).reshape(4, 8).cpu().tolist()
-            print(f"M={M:2d} N={N:5d} K={K:5d} b2b={int(back_to_back)} ctas={int(used.sum())} total={e0.elapsed_time(e1)*1e3:7.1f}us "
-                  f"entry_spread={(gt.max()-gt.min()).item()/1e3:5.2f}us  med(cyc)={[int(v) for v in med]}  max={[int(v) for v in mx]}")
-            if not back_to_back:
-                print("     units 8..11 of CTA0 [wfull, math_done, aempty_ok, st_done, arrived, mma_start, mma_issued]:")
-                for row in fine:
-                    print("      ", row[:7])
+        ws_list = [mk(N, K) for _ in range(4)]
+        for _ in range(2):
+            ops.int4_tilepacked_linear(x, ws_list[0][0], g, ws_list[0][1], None, N, 1)
+        torch.cuda.synchronize()
+        ws = ops.debug_workspace(x)
+        ws[48 * 1024: 64 * 1024].zero_()
+        torch.cuda.synchronize()
+        for c in range(4):   # chain of 4; slots hold launches 2 and 3 (or 3 and 2)
+            ops.int4_tilepacked_linear(x, ws_list[c][0], g, ws_list[c][1], None, N, 1)
+        torch.cuda.synchronize()
+        a, b = slot(ws, 0), slot(ws, 1)
+        ua, ub = a[a[:, 7] > 0], b[b[:, 7] > 0]
+        first, second = (ua, ub) if ua[:, 0].min() < ub[:, 0].min() else (ub, ua)
+        t0 = int(first[:, 0].min())
+        print(f"M={M} N={N} K={K}: chain of 4, last two kernels (us since the earlier one's first CTA entry; min / median / max over CTAs)")
+        for nm, kern in (("k", first), ("k+1", second)):
+            parts = []
+            for e in range(8):
+                col = (kern[:, e] - t0).float() / 1e3
+                parts.append(f"{names[e]} {col.min():.1f}/{col.median():.1f}/{col.max():.1f}")
+            print(f"   {nm:4s}" + "  ".join(parts))
+        print(f"   launch-to-launch: {(int(second[:, 7].max()) - int(first[:, 7].max())) / 1e3:.2f} us  (end of k+1 minus end of k)")
