@@ -89,7 +89,10 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   uint32_t* flag_slot = tmem_slot + 1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle => known warp-uniform: the single-thread roles are warp-uniform loops with only
+  // the TMA / tcgen05 instructions under elect.sync, so their operands live in uniform registers (with the whole
+  // loop under `lane == 0` ptxas wraps every UTCHMMA / UTMALDG in an elect-broadcast loop, ~2.5x slower issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
   const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
   const int u0 = unit_begin(b, U, G), u1 = unit_begin(b + 1, U, G);
@@ -117,11 +120,11 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_launch_dependents();
 
   if (warp == TMA_WARP) {
-    if (lane == 0) {
+    {
       const uint64_t pol_w = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
       auto issue_w = [&](int i) {
@@ -154,13 +157,22 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         }
       };
       const int pre = nunits < S ? nunits : S;
-      for (int i = 0; i < pre; ++i) issue_w(i);
+      for (int i = 0; i < pre; ++i) {
+        if (elect_one()) issue_w(i);   // weights never depend on the previous kernel
+        __syncwarp();
+      }
       pdl_wait();
-      for (int i = 0; i < pre; ++i) issue_x(i);
+      for (int i = 0; i < pre; ++i) {
+        if (elect_one()) issue_x(i);
+        __syncwarp();
+      }
       for (int i = S; i < nunits; ++i) {
         mbar_wait(&sempty[i % S], ((i / S) & 1) ^ 1);
-        issue_w(i);
-        issue_x(i);
+        if (elect_one()) {
+          issue_w(i);
+          issue_x(i);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == MMA_WARP) {
@@ -182,7 +194,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       mbar_wait(&wfull[s], (i / S) & 1);
       mbar_wait(&xfull[s], (i / S) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t ab = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
         const uint32_t bb = ab + A_BYTES;
         const uint32_t d_t = tmem_base + (buf ? C::D_COL1 : C::D_COL0);

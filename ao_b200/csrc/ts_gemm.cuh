@@ -469,6 +469,20 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
               const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
               return p.ws_partial + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + r;
             };
+            if (p.M - m0 == 1) {
+              // decode, one token column: every contributor's value in flight at once (one L2 round trip per 8)
+              float acc = 0.f;
+#pragma unroll 1
+              for (int bb = b_first; bb <= b_last; bb += 8) {
+                float t[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) t[c] = (bb + c <= b_last) ? __ldcg(slot_of(bb + c)) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc += t[c];
+              }
+              if (p.row_scale) acc *= p.row_scale[m0];
+              p.y[(size_t)m0 * p.N_out + n] = __float2bfloat16_rn(acc * osc + bias);
+            } else
 #pragma unroll 1
             for (int j0 = 0; j0 < N_MMA; j0 += 8) {
               if (m0 + j0 >= p.M) break;
