@@ -316,6 +316,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           __threadfence();
           const int b_first = cta_of_unit(tile * p.KT, U, G);
           const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
+          const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
           if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;
           if (n < p.N) {
 #pragma unroll 1
@@ -328,13 +329,34 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
                 vf[q] = 0.f;
                 vi[q] = 0;
               }
-              for (int bb = b_first; bb <= b_last; ++bb) {  // fixed order: deterministic
-                const int wh = (unit_begin(bb, U, G) / p.KT == tile) ? 0 : 1;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.ws_partial) +
-                                      ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + (size_t)j0 * ROWS + r;
+              // fixed CTA order => deterministic; two contributors' loads in flight together (the gather is a chain of
+              // L2 round trips).  Only the first contributor can have started in an earlier tile (its tail slot).
+              auto slot_of = [&](int bb) {
+                const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
+                return reinterpret_cast<const uint32_t*>(p.ws_partial) + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) +
+                       (size_t)j0 * ROWS + r;
+              };
+              int bb = b_first;
+#pragma unroll 1
+              for (; bb + 1 <= b_last; bb += 2) {
+                const uint32_t* s0 = slot_of(bb);
+                const uint32_t* s1 = slot_of(bb + 1);
+                uint32_t t0[16], t1[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) t0[q] = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0u;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) t1[q] = (m0 + j0 + q < p.M) ? __ldcg(s1 + q * ROWS) : 0u;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                  const uint32_t v = __ldcg(src + q * ROWS);
+                  vi[q] += (int32_t)t0[q] + (int32_t)t1[q];
+                  vf[q] = (vf[q] + __uint_as_float(t0[q])) + __uint_as_float(t1[q]);
+                }
+              }
+              if (bb <= b_last) {
+                const uint32_t* s0 = slot_of(bb);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const uint32_t v = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0u;
                   vi[q] += (int32_t)v;
                   vf[q] += __uint_as_float(v);
                 }
@@ -398,8 +420,11 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   p.sf_col_blocks_x = ceil_div(sf_per_row, 4);
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
+  // (8 when more than 8 token columns are reduced: finer splits lengthen the split-tile reduction more than they
+  // shorten the streaming phase)
   int grid = sm_count();
-  if (units / 4 < grid) grid = units / 4 > 0 ? (int)(units / 4) : 1;
+  const int min_units = M <= 8 ? 4 : 8;
+  if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)
     return fail(AO_ERR_WORKSPACE, "lowp linear: workspace too small (%zu < %zu)", ws_bytes, need);

@@ -261,8 +261,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);  // MMAs of chunk i - T are done
       tc_fence_after();
       if ((warp & 3) == 0 && lane == 0) stamp2(i, 2);
-      tmem_st_x32(a_t, out);
-      tc_wait_st();   // the registers are reused by the second half
+      tmem_st_x32(a_t, out);   // source registers are consumed at issue: no tcgen05.wait::st before reusing them
       Fmt::dequant_half(p, st, st + W_BYTES, r, 1, out);
       __syncwarp();
       if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
