@@ -169,6 +169,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   uint64_t* dempty = dfull + 2;       // [2]   4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   uint32_t* flag_slot = tmem_slot + 1;
+  uint32_t* coop_slot = tmem_slot + 2;
 
   // The warp index goes through a shuffle so that the compiler knows it is warp-uniform: the single-thread
   // roles below run as warp-uniform loops with only the tcgen05 / TMA / mbarrier instruction itself under
@@ -199,6 +200,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   const int nunits = u1 - u0;
 
   if (threadIdx.x == 0) {
+    *coop_slot = 0;
     for (int i = 0; i < S; ++i) {
       mbar_init(&wfull[i], 1);
       mbar_init(&sempty[i], 4);
@@ -229,6 +231,81 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   // unit i of this CTA -> (tile, kc); tiles are (m_blk, n_tile) pairs, n_tile fastest
   auto tile_of = [&](int i) { return (u0 + i) / p.KT; };
   auto kc_of = [&](int i) { return (u0 + i) % p.KT; };
+
+  // Split-tile reduction of one tile by this CTA (it completed the tile's unit counter): sums the contributors'
+  // partials in CTA order -- fixed order, so bit-reproducible whoever finishes -- and writes output row r of the
+  // column groups g = helper, helper + nhelp, ... (8 token columns each).  The gather is a chain of L2 round trips, so
+  // what counts is loads in flight: two contributors x 8 columns per step and, for the CTA's last segment, three
+  // warpgroups sharing the column groups (the dequant warpgroups are idle by then).
+  auto finish_tile = [&](int tile, int r, int helper, int nhelp) {
+    const int b_first = cta_of_unit(tile * p.KT, U, G);
+    const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
+    const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
+    const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+    const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
+    if (n >= p.N_out) return;
+    const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+    const float osc = p.out_scale ? *p.out_scale : 1.f;
+    auto slot_of = [&](int bb) {
+      // only the first contributor can have started in an earlier tile (then this is its tail slot)
+      const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
+      return p.ws_partial + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + r;
+    };
+    if (p.M - m0 == 1) {
+      // decode, one token column: every contributor's value in flight at once (one L2 round trip per 8)
+      if (helper != 0) return;
+      float acc = 0.f;
+#pragma unroll 1
+      for (int bb = b_first; bb <= b_last; bb += 8) {
+        float t[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = (bb + c <= b_last) ? __ldcg(slot_of(bb + c)) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc += t[c];
+      }
+      if (p.row_scale) acc *= p.row_scale[m0];
+      p.y[(size_t)m0 * p.N_out + n] = __float2bfloat16_rn(acc * osc + bias);
+      return;
+    }
+#pragma unroll 1
+    for (int j0 = helper * 8; j0 < N_MMA; j0 += nhelp * 8) {
+      if (m0 + j0 >= p.M) break;
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = 0.f;
+      int bb = b_first;
+#pragma unroll 1
+      for (; bb + 1 <= b_last; bb += 2) {
+        const float* s0 = slot_of(bb) + (size_t)j0 * ROWS;
+        const float* s1 = slot_of(bb + 1) + (size_t)j0 * ROWS;
+        float t0[8], t1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t0[q] = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t1[q] = (m0 + j0 + q < p.M) ? __ldcg(s1 + q * ROWS) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (v[q] + t0[q]) + t1[q];
+      }
+      if (bb <= b_last) {
+        const float* s0 = slot_of(bb) + (size_t)j0 * ROWS;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int m = m0 + j0 + q;
+        if (m < p.M) {
+          float t = v[q];
+          if (p.row_scale) t *= p.row_scale[m];
+          p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(t * osc + bias);
+        }
+      }
+    }
+  };
+  // hand-over of the CTA's last split-tile reduction to all three warpgroups: coop_slot = tile + 1, or 0
+  // (only when several column groups exist to share: with <= 8 token columns the hand-over costs more than it saves)
+  const bool use_coop = p.M > 8;
+  auto coop_barrier = [&]() { asm volatile("bar.sync 2, 384;" ::: "memory"); };
 
   if (warp < DEQ_WARPS) {
     // ------------------------------------------------------------ dequant warpgroups (0: even, 1: odd chunks)
@@ -276,6 +353,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (s >= S) { s -= S; sph ^= 1; }
       t += 2;
       if (t >= T) { t -= T; ++k; }
+    }
+    // help with the CTA's last split-tile reduction, if this CTA turns out to be the one completing that tile
+    if (use_coop) coop_barrier();
+    const uint32_t ct = use_coop ? *coop_slot : 0u;
+    if (ct) {
+      __threadfence();
+      finish_tile((int)ct - 1, r, 1 + wg, 3);
     }
   } else if (warp >= TMA_WARP) {
     if (warp == TMA_WARP) {
@@ -372,6 +456,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     pdl_wait();
     int seg = 0;
     int i = 0;
+    bool coop = false;
     while (i < nunits) {
       const int tile = tile_of(i);
       const int kc_first = kc_of(i);
@@ -456,72 +541,21 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot is rewritten by the next segment
         if (finish) {
           __threadfence();
-          const int b_first = cta_of_unit(tile * p.KT, U, G);
-          const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
-          const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
           if ((warp == EPI_WARP0 && lane == 0)) p.ws_sem[tile] = 0;  // restore for the next launch
-          if (n < p.N_out) {
-            // fixed CTA order => bit-reproducible whoever finishes.  8 columns at a time, two contributors' loads
-            // in flight together: the gather is a chain of L2 round trips, so memory-level parallelism is what counts
-            auto slot_of = [&](int bb) {
-              // only the first contributor can have started in an earlier tile (then this is its tail slot)
-              const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
-              return p.ws_partial + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) + r;
-            };
-            if (p.M - m0 == 1) {
-              // decode, one token column: every contributor's value in flight at once (one L2 round trip per 8)
-              float acc = 0.f;
-#pragma unroll 1
-              for (int bb = b_first; bb <= b_last; bb += 8) {
-                float t[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) t[c] = (bb + c <= b_last) ? __ldcg(slot_of(bb + c)) : 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc += t[c];
-              }
-              if (p.row_scale) acc *= p.row_scale[m0];
-              p.y[(size_t)m0 * p.N_out + n] = __float2bfloat16_rn(acc * osc + bias);
-            } else
-#pragma unroll 1
-            for (int j0 = 0; j0 < N_MMA; j0 += 8) {
-              if (m0 + j0 >= p.M) break;
-              float v[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = 0.f;
-              int bb = b_first;
-#pragma unroll 1
-              for (; bb + 1 <= b_last; bb += 2) {
-                const float* s0 = slot_of(bb) + (size_t)j0 * ROWS;
-                const float* s1 = slot_of(bb + 1) + (size_t)j0 * ROWS;
-                float t0[8], t1[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t0[q] = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t1[q] = (m0 + j0 + q < p.M) ? __ldcg(s1 + q * ROWS) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (v[q] + t0[q]) + t1[q];
-              }
-              if (bb <= b_last) {
-                const float* s0 = slot_of(bb) + (size_t)j0 * ROWS;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] += (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0.f;
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int m = m0 + j0 + q;
-                if (m < p.M) {
-                  float t = v[q];
-                  if (p.row_scale) t *= p.row_scale[m];
-                  p.y[(size_t)m * p.N_out + n] = __float2bfloat16_rn(t * osc + bias);
-                }
-              }
-            }
+          if (use_coop && i + cnt >= nunits) {
+            // the CTA's last segment: the reduction is on the kernel's critical path, share it (see finish_tile)
+            if (warp == EPI_WARP0 && lane == 0) *coop_slot = (uint32_t)tile + 1u;
+            coop = true;
+          } else {
+            finish_tile(tile, r, 0, 1);
           }
         }
       }
       i += cnt;
       ++seg;
     }
+    if (use_coop) coop_barrier();
+    if (coop) finish_tile((int)*coop_slot - 1, r, 0, 3);
     if ((warp == EPI_WARP0 && lane == 0)) stamp(7);
   }
 
