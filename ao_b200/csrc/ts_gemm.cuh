@@ -235,8 +235,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   // Split-tile reduction of one tile by this CTA (it completed the tile's unit counter): sums the contributors'
   // partials in CTA order -- fixed order, so bit-reproducible whoever finishes -- and writes output row r of the
   // column groups g = helper, helper + nhelp, ... (8 token columns each).  The gather is a chain of L2 round trips, so
-  // what counts is loads in flight: two contributors x 8 columns per step and, for the CTA's last segment, three
-  // warpgroups sharing the column groups (the dequant warpgroups are idle by then).
+  // what counts is loads in flight: two contributors x 8 columns per step and, for the CTA's last segment, all four
+  // warpgroups sharing the column groups (dequant warps, producers and issuer are idle by then).
   auto finish_tile = [&](int tile, int r, int helper, int nhelp) {
     const int b_first = cta_of_unit(tile * p.KT, U, G);
     const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
@@ -302,10 +302,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       }
     }
   };
-  // hand-over of the CTA's last split-tile reduction to all three warpgroups: coop_slot = tile + 1, or 0
+  // hand-over of the CTA's last split-tile reduction to all four warpgroups: coop_slot = tile + 1, or 0
   // (only when several column groups exist to share: with <= 8 token columns the hand-over costs more than it saves)
   const bool use_coop = p.M > 8;
-  auto coop_barrier = [&]() { asm volatile("bar.sync 2, 384;" ::: "memory"); };
+  auto coop_barrier = [&]() { asm volatile("bar.sync 2, 512;" ::: "memory"); };
 
   if (warp < DEQ_WARPS) {
     // ------------------------------------------------------------ dequant warpgroups (0: even, 1: odd chunks)
@@ -359,7 +359,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const uint32_t ct = use_coop ? *coop_slot : 0u;
     if (ct) {
       __threadfence();
-      finish_tile((int)ct - 1, r, 1 + wg, 3);
+      finish_tile((int)ct - 1, r, 1 + wg, 4);
     }
   } else if (warp >= TMA_WARP) {
     if (warp == TMA_WARP) {
@@ -446,6 +446,15 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         i += cnt;
         ++seg;
         kc0 = 0;
+      }
+    }
+    // fourth helper warpgroup of the CTA's last split-tile reduction (producers and issuer are done by then)
+    if (use_coop) {
+      coop_barrier();
+      const uint32_t ct = *coop_slot;
+      if (ct) {
+        __threadfence();
+        finish_tile((int)ct - 1, (warp & 3) * 32 + lane, 3, 4);
       }
     }
   } else {
@@ -555,7 +564,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       ++seg;
     }
     if (use_coop) coop_barrier();
-    if (coop) finish_tile((int)*coop_slot - 1, r, 0, 3);
+    if (coop) finish_tile((int)*coop_slot - 1, r, 0, 4);
     if ((warp == EPI_WARP0 && lane == 0)) stamp(7);
   }
 
