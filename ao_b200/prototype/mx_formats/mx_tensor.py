@@ -16,9 +16,11 @@ import torch
 
 from ao_b200.quantization.quantize_.common.kernel_preference import KernelPreference
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
-from ao_b200.utils import TorchAOBaseTensor
+from torch.utils._python_dispatch import return_and_correct_aliasing
 
-from .utils import from_blocked, hp_data_dims_to_swizzled_scale_dims_mx
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+
+from .utils import from_blocked, hp_data_dims_to_swizzled_scale_dims_mx, slice_qdata_and_scale
 
 aten = torch.ops.aten
 __all__ = ["MXTensor", "ScaleCalculationMode", "QuantizeTensorToMXKwargs"]
@@ -128,6 +130,26 @@ def _(func, types, args, kwargs):
                         k.kernel_preference, None, True)
     y = torch.ops.ao_b200.mxfp8_linear(xq.qdata, xq.scale.view(torch.uint8), w.qdata, w.scale.view(torch.uint8), bias)
     return y.reshape(*orig_shape[:-1], N).to(x.dtype)
+
+
+@implements(aten.slice.Tensor)
+def _(func, types, args, kwargs):
+    """Row / column slices (`narrow`-style tensor-parallel loaders); reference `mx_slice`."""
+    self, dim, start, end, step = fill_defaults(args, 5, [0, None, None, 1])
+    if step != 1:
+        raise ValueError("Only support aten.slice with step=1")
+    qd, sc = slice_qdata_and_scale(self, dim, start, end)
+    return return_and_correct_aliasing(func, args, kwargs, MXTensor(qd, sc, self.elem_dtype, self.block_size, self.orig_dtype, self.kernel_preference, self.act_quant_kwargs, self.is_swizzled_scales))
+
+
+@implements(aten.select.int)
+def _(func, types, args, kwargs):
+    self, dim, index = args
+    assert dim == 0, f"MXTensor aten.select.int with {dim=} is not yet supported"
+    assert self.qdata.dim() == self.scale.dim(), "unsupported"
+    assert not self.is_swizzled_scales, "unsupported"
+    qd, sc = self.qdata[index], self.scale[index]
+    return return_and_correct_aliasing(func, args, kwargs, MXTensor(qd, sc, self.elem_dtype, self.block_size, self.orig_dtype, self.kernel_preference, self.act_quant_kwargs, self.is_swizzled_scales))
 
 
 MXTensor.__module__ = "ao_b200.prototype.mx_formats"

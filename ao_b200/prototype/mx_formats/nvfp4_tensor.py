@@ -16,9 +16,11 @@ from typing import Optional
 import torch
 
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
-from ao_b200.utils import TorchAOBaseTensor
+from torch.utils._python_dispatch import return_and_correct_aliasing
 
-from .utils import from_blocked
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+
+from .utils import from_blocked, slice_qdata_and_scale
 
 aten = torch.ops.aten
 F4_E2M1_MAX = 6.0
@@ -146,6 +148,26 @@ class QuantizeTensorToFloat8ActKwargs(QuantizeTensorKwargs):
     """Activation recipe for the nvfp4-weight x fp8-activation linear: e4m3, per-token scale."""
 
     float8_dtype: torch.dtype = torch.float8_e4m3fn
+
+
+@implements(aten.slice.Tensor)
+def _(func, types, args, kwargs):
+    """Row / column slices (`narrow`-style tensor-parallel loaders); reference `nvfp4_slice`."""
+    self, dim, start, end, step = fill_defaults(args, 5, [0, None, None, 1])
+    if step != 1:
+        raise ValueError("Only support aten.slice with step=1")
+    qd, sc = slice_qdata_and_scale(self, dim, start, end)
+    return return_and_correct_aliasing(func, args, kwargs, NVFP4Tensor(qd, sc, self.block_size, self.orig_dtype, self.per_tensor_scale, self.act_per_tensor_scale, self.is_swizzled_scales, self.use_triton_kernel, self.act_quant_kwargs))
+
+
+@implements(aten.select.int)
+def _(func, types, args, kwargs):
+    self, dim, index = args
+    assert dim == 0, f"NVFP4Tensor aten.select.int with {dim=} is not yet supported"
+    assert self.qdata.dim() == self.scale.dim(), "unsupported"
+    assert not self.is_swizzled_scales, "unsupported"
+    qd, sc = self.qdata[index], self.scale[index]
+    return return_and_correct_aliasing(func, args, kwargs, NVFP4Tensor(qd, sc, self.block_size, self.orig_dtype, self.per_tensor_scale, self.act_per_tensor_scale, self.is_swizzled_scales, self.use_triton_kernel, self.act_quant_kwargs))
 
 
 NVFP4Tensor.__module__ = "ao_b200.prototype.mx_formats"
