@@ -86,6 +86,26 @@ Tensor int4_dequant_tile4d(const Tensor& qdata, const Tensor& scale_and_zero, in
   return out;
 }
 
+// w bf16 [N, K] -> (q uint8 [N, K], scale bf16 [N, K/g], zero bf16 [N, K/g])  (HQQ solver, tinygemm convention)
+std::tuple<Tensor, Tensor, Tensor> int4_hqq_quantize(const Tensor& w, int64_t group_size) {
+  check_cuda(w, "w");
+  TORCH_CHECK(w.scalar_type() == at::kBFloat16 && w.dim() == 2, "ao_b200: w must be bf16 [N, K]");
+  c10::cuda::CUDAGuard guard(w.device());
+  const int64_t N = w.size(0), K = w.size(1);
+  TORCH_CHECK(K % group_size == 0, "ao_b200: K=", K, " must be a multiple of group_size=", group_size);
+  Tensor q = at::empty({N, K}, w.options().dtype(at::kByte));
+  Tensor s = at::empty({N, K / group_size}, w.options());
+  Tensor z = at::empty({N, K / group_size}, w.options());
+  Tensor ws = at::empty({(int64_t)ao_int4_hqq_workspace_bytes((int)N, (int)K, (int)group_size)}, w.options().dtype(at::kByte));
+  AO_CALL(ao_int4_hqq_quantize(bf16_ptr(w), (int)N, (int)K, (int)group_size, q.data_ptr<uint8_t>(), bf16_ptr_mut(s),
+                               bf16_ptr_mut(z), ws.data_ptr(), (size_t)ws.numel(), cur_stream()));
+  return {q, s, z};
+}
+std::tuple<Tensor, Tensor, Tensor> int4_hqq_quantize_meta(const Tensor& w, int64_t group_size) {
+  return {at::empty({w.size(0), w.size(1)}, w.options().dtype(at::kByte)),
+          at::empty({w.size(0), w.size(1) / group_size}, w.options()), at::empty({w.size(0), w.size(1) / group_size}, w.options())};
+}
+
 // x [M, K] bf16 -> y [M, n_out] bf16  (aten._weight_int4pack_mm + bias + out-feature slice)
 Tensor int4_tilepacked_linear(const Tensor& x, const Tensor& qdata, int64_t group_size,
                               const Tensor& scale_and_zero, const c10::optional<Tensor>& bias,
@@ -142,6 +162,7 @@ TORCH_LIBRARY(ao_b200, m) {
   m.def("int4_pack_tile4d(Tensor q_u8, int inner_k_tiles) -> Tensor");
   m.def("int4_unpack_tile4d(Tensor qdata) -> Tensor");
   m.def("int4_dequant_tile4d(Tensor qdata, Tensor scale_and_zero, int group_size) -> Tensor");
+  m.def("int4_hqq_quantize(Tensor w, int group_size) -> (Tensor, Tensor, Tensor)");
   m.def("int4_tilepacked_linear(Tensor x, Tensor qdata, int group_size, Tensor scale_and_zero, Tensor? bias, int n_out=0, int impl=0) -> Tensor");
   m.def("launch_count() -> int", []() -> int64_t { return (int64_t)ao_b200_launch_count(); });
   m.def("debug_workspace(Tensor like) -> Tensor", [](const at::Tensor& like) { return workspace_for(like); });
@@ -152,6 +173,7 @@ TORCH_LIBRARY_IMPL(ao_b200, CUDA, m) {
   m.impl("int4_pack_tile4d", &int4_pack_tile4d);
   m.impl("int4_unpack_tile4d", &int4_unpack_tile4d);
   m.impl("int4_dequant_tile4d", &int4_dequant_tile4d);
+  m.impl("int4_hqq_quantize", &int4_hqq_quantize);
   m.impl("int4_tilepacked_linear", &int4_tilepacked_linear);
   ao_b200_impl_lowp_cuda(m);
 }
@@ -160,6 +182,7 @@ TORCH_LIBRARY_IMPL(ao_b200, Meta, m) {
   m.impl("int4_pack_tile4d", &int4_pack_tile4d_meta);
   m.impl("int4_unpack_tile4d", &int4_unpack_tile4d_meta);
   m.impl("int4_dequant_tile4d", &int4_dequant_tile4d_meta);
+  m.impl("int4_hqq_quantize", &int4_hqq_quantize_meta);
   m.impl("int4_tilepacked_linear", &int4_tilepacked_linear_meta);
   ao_b200_impl_lowp_meta(m);
 }

@@ -59,16 +59,22 @@ class Int4TilePackedTo4dTensor(TorchAOBaseTensor):
         assert hp_tensor.dim() == 2, "Int4TilePackedTo4dTensor: 2-D weights only"
         if not hp_tensor.is_cuda:
             raise ValueError("Int4TilePackedTo4dTensor.from_hp needs a CUDA tensor (the packing kernel is sm_100a CUDA)")
-        if int4_choose_qparams_algorithm != Int4ChooseQParamsAlgorithm.TINYGEMM:
-            raise NotImplementedError("HQQ qparams are SURVEY §8(f)-2 'next'; only TINYGEMM is implemented")
         original_shape = hp_tensor.shape
         N0, K0 = original_shape
         g = block_size[-1]
         K = find_multiple(K0, 1024)
         N = find_multiple(N0, ntile_size or 8)
         w = torch.nn.functional.pad(hp_tensor, (0, K - K0, 0, N - N0))
-        scale, zero = choose_qparams_affine_tinygemm(w, g)
-        q = quantize_affine_tinygemm(w, g, scale, zero)
+        if int4_choose_qparams_algorithm == Int4ChooseQParamsAlgorithm.HQQ:
+            # reference :149-167 -> _choose_qparams_and_quantize_affine_hqq (quant_primitives.py:1797-2002); here one
+            # CUDA solver (ao_b200/csrc/int4_hqq.cu), scale / zero already in the tinygemm convention
+            q, scale, zero = torch.ops.ao_b200.int4_hqq_quantize(w.contiguous(), g)
+            q = q.to(torch.int32)
+        else:
+            assert int4_choose_qparams_algorithm == Int4ChooseQParamsAlgorithm.TINYGEMM, (
+                f"Unsupported Int4ChooseQParamsAlgorithm: {int4_choose_qparams_algorithm}")
+            scale, zero = choose_qparams_affine_tinygemm(w, g)
+            q = quantize_affine_tinygemm(w, g, scale, zero)
         q_u8 = (q[:, ::2] << 4 | q[:, 1::2]).to(torch.uint8).contiguous()
         qdata = torch.ops.ao_b200.int4_pack_tile4d(q_u8, INNER_K_TILES)
         scale_and_zero = pack_tinygemm_scales_and_zeros(scale, zero, scale.dtype)

@@ -54,6 +54,18 @@ uint64_t ao_b200_launch_count(void);
  * out: int32 [N/8][K/(inner_k_tiles*16)][32][inner_k_tiles/2]                     */
 int ao_int4_pack_tile4d(const uint8_t* q_u8, int32_t* qdata, int N, int K,
                         int inner_k_tiles, void* stream);
+/* HQQ qparams + 4-bit codes for a bf16 weight (the reference's int4 benchmark recipe:
+ * Int4WeightOnlyConfig(int4_choose_qparams_algorithm="hqq")).  Replaces
+ * _choose_qparams_and_quantize_affine_hqq + optimize_weights_proximal_legacy
+ * (quantization/quant_primitives.py:1797-2002) as called at
+ * quantize_/workflows/int4/int4_tile_packed_to_4d_tensor.py:149-167 (nbits 4, axis 1, raw_output False).
+ * in : w bf16 [N][K] (already padded), group_size in {32,64,128,256} dividing K
+ * out: q uint8 [N][K] (one code 0..15 per byte), scale / zero bf16 [N][K/group_size] in the tinygemm
+ *      convention W^ = (q - 8) * scale + zero
+ * workspace: device scratch of ao_int4_hqq_workspace_bytes(N, K, group_size) bytes (not shared with the linears). */
+size_t ao_int4_hqq_workspace_bytes(int N, int K, int group_size);
+int ao_int4_hqq_quantize(const uint16_t* w, int N, int K, int group_size, uint8_t* q, uint16_t* scale,
+                         uint16_t* zero, void* workspace, size_t workspace_bytes, void* stream);
 /* Inverse of the above: qdata -> q_u8[N][K/2] (used by dequantize() and tests). */
 int ao_int4_unpack_tile4d(const int32_t* qdata, uint8_t* q_u8, int N, int K,
                           int inner_k_tiles, void* stream);

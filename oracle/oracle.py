@@ -98,6 +98,18 @@ def int4_quantize(w_bits, g, s, z):
     return q
 
 
+def int4_hqq(w_bits: np.ndarray, g: int):
+    """HQQ int4 codes [N, K] (one per byte) + tinygemm-convention scale / zero (bf16 bits, [N, K/g]); also the
+    number of solver iterations run."""
+    N, K = w_bits.shape
+    q = np.empty((N, K), np.uint8)
+    s = np.empty((N, K // g), np.uint16)
+    z = np.empty((N, K // g), np.uint16)
+    lib().ao_oracle_int4_hqq.restype = C.c_int
+    iters = lib().ao_oracle_int4_hqq(_p(_c(w_bits, np.uint16)), N, K, g, _p(q), _p(s), _p(z))
+    return q, s, z, int(iters)
+
+
 def pack_scales_and_zeros(s, z):
     N, KG = s.shape
     out = np.empty((KG, N, 2), np.uint16)

@@ -35,6 +35,10 @@ def test_c_abi_argument_validation_without_gpu():
     assert rc == -1 and b"group_size" in lib.ao_b200_last_error()
     rc = lib.ao_int4_pack_tile4d(None, None, 12, 128, 8, None)
     assert rc == -1
+    rc = lib.ao_int4_hqq_quantize(None, 8, 1024, 48, None, None, None, None, ctypes.c_size_t(0), None)
+    assert rc == -1 and b"group_size" in lib.ao_b200_last_error()
+    lib.ao_int4_hqq_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.ao_int4_hqq_workspace_bytes(4096, 4096, 32) >= 2 * 4 * 4096 * 128
     rc = lib.ao_fp8_rowwise_linear(None, None, 4, 4096, None, None, 100, None, None, None, ctypes.c_size_t(0), None)
     assert rc == -1 and b"multiple of 16" in lib.ao_b200_last_error()
     # M == 0 is a no-op success (reference: empty-input short circuit, int4_tile_packed_to_4d_tensor.py:284-285)
@@ -51,6 +55,8 @@ def test_torch_ops_registered_with_meta_kernels():
     assert torch.ops.ao_b200.int4_tilepacked_linear(x, qd, 32, sz, None, 100).shape == (3, 100)
     q, s = torch.ops.ao_b200.int8_quantize_rowwise(x)
     assert q.dtype == torch.int8 and s.shape == (3, 1)
+    q4, s4, z4 = torch.ops.ao_b200.int4_hqq_quantize(x, 64)
+    assert q4.shape == (3, 1024) and q4.dtype == torch.uint8 and s4.shape == z4.shape == (3, 16) and s4.dtype == torch.bfloat16
     q, s = torch.ops.ao_b200.mxfp8_quantize(x, True)
     assert s.shape == (32, 16 * 8)
     q, s = torch.ops.ao_b200.nvfp4_quantize(x, None, True)
