@@ -5,6 +5,8 @@ Bit-exact: packing, unpacking, qparams, q, scale_and_zero, dequant.  GEMM output
 oracle's exact-product fp64-accumulated result >= 45 dB (bf16 output rounding is ~55 dB) and
 >= 80 dB vs aten._weight_int4pack_mm when that op is available (the reference's own kernel).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
