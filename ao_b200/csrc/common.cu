@@ -99,6 +99,16 @@ int ts_ctas_per_sm() {
   return v;
 }
 
+int ts_min_units() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_TS_MIN_UNITS");
+    v = e ? atoi(e) : 0;   // 0 = choose per problem size
+    if (v < 0 || v > 64) v = 0;
+  }
+  return v;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

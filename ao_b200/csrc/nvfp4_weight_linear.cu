@@ -116,7 +116,7 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
   // small problems: at least 4 (decode, one token column to reduce) or 8 chunks per CTA: splitting a tile over
   // more CTAs shortens the streaming phase but lengthens the split-tile reduction, a chain of L2 round trips
-  const int min_units = M <= 8 ? 4 : 8;
+  const int min_units = ts_min_units() ? ts_min_units() : (M <= 8 ? 4 : 8);
   if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)

@@ -238,9 +238,9 @@ def run_ours(args):
                 "e2e_value": world * 1 / (bs1["ms_per_step_e2e"] * 1e-3),
                 "roofline_frac": _algo_bytes(shape, layers, 1) / (bs1["ms_per_step"] * 1e-3) / 1e9 / peak},
         # traffic: dram__bytes_read+write per launch from the ncu --set full capture of this kernel on the seven
-        # Llama-3-8B shapes at bs=32 (profiles/r01_int4_final_ncu.md): 139.1 MB per layer / 7 launches
+        # Llama-3-8B shapes at bs=32 (profiles/r01_int4_final_ncu.md): 139.3 MB per layer / 7 launches
         "roofline": {"bound": "hbm", "kernel": "ao::tsg::ts_gemm_kernel<ao::int4k::Int4Fmt, 32>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": 19.87e6 if args.bs == 32 else None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": 19.90e6 if args.bs == 32 else None,
                      "algorithmic_bytes_per_launch": ab / max(1, kernel_launches), "peak_source": peak_src,
                      "algorithmic_bytes_per_step": ab, "launches_per_step": kernel_launches},
         "finite_outputs": main["finite"],
