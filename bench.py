@@ -260,6 +260,7 @@ def _cpu_sample(bs, layers_sampled, threads):
     from oracle import oracle as o
 
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    o.lib().ao_oracle_set_threads(int(threads))   # torchrun exports OMP_NUM_THREADS=1 before we start
     rng = np.random.default_rng(0)
     shape = LLAMA3_8B
     mats = []
