@@ -422,8 +422,11 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
   // (8 when more than 8 token columns are reduced: finer splits lengthen the split-tile reduction more than they
   // shorten the streaming phase)
-  int grid = sm_count();
-  const int min_units = M <= 8 ? 4 : 8;
+  // two CTAs per SM where they fit (N_MMA <= 64): this kernel has no dequant phase, it is bounded by the bytes in
+  // flight per SM (stages x 16-20 KB against the DRAM round trip), which a second resident CTA doubles
+  const int per_sm = (N_MMA <= 64) ? (ts_ctas_per_sm() ? ts_ctas_per_sm() : 2) : 1;
+  int grid = sm_count() * per_sm;
+  const int min_units = ts_min_units() ? ts_min_units() : (M <= 8 ? 4 : 8);
   if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
   const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)

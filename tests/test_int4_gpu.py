@@ -236,3 +236,32 @@ def test_hqq_through_quantize_api_beats_tinygemm_qparams():
     sq_h, we_h = run("hqq")
     assert sq_h > 20.0 and sq_t > 20.0
     assert we_h <= we_t * 1.001, (we_h, we_t)
+
+
+# ------------------------------------------------------------------ op registration contract
+@pytest.mark.gpu
+def test_ops_pass_opcheck_and_survive_fullgraph_tracing():
+    """The reference requires its extern ops to pass torch.library.opcheck (schema, fake kernel, functionalisation) and
+    to survive torch.compile(fullgraph=True) (test/test_ops.py, test_float8_tensor.py:397).  Tracing uses the
+    aot_eager backend: the graph is captured with fake tensors and our Meta kernels, then runs our CUDA ops."""
+    import torch
+
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import Int4WeightOnlyConfig, quantize_
+
+    torch.manual_seed(0)
+    x = torch.randn(4, 1024, device="cuda", dtype=torch.bfloat16)
+    lin = torch.nn.Linear(1024, 256, bias=True, device="cuda", dtype=torch.bfloat16)
+    quantize_(lin, Int4WeightOnlyConfig(group_size=32, int4_packing_format="tile_packed_to_4d"))
+    w = lin.weight
+    tests = ("test_schema", "test_faketensor")
+    torch.library.opcheck(torch.ops.ao_b200.int4_tilepacked_linear.default, (x, w.qdata, 32, w.scale_and_zero, lin.bias, 256, 0),
+                          test_utils=tests)
+    torch.library.opcheck(torch.ops.ao_b200.int8_quantize_rowwise.default, (x,), test_utils=tests)
+    torch.library.opcheck(torch.ops.ao_b200.mxfp8_quantize.default, (x, True), test_utils=tests)
+    torch.library.opcheck(torch.ops.ao_b200.int4_hqq_quantize.default, (x, 32), test_utils=tests)
+
+    y_eager = lin(x)
+    compiled = torch.compile(lin, fullgraph=True, backend="aot_eager")
+    y_comp = compiled(x)
+    assert torch.equal(y_eager, y_comp)
