@@ -26,8 +26,9 @@ class AOBaseConfig(abc.ABC):
     version: int = 1
 
 
-ALLOWED_AO_MODULES = {
-    "ao_b200",
+# Modules searched, in order, for the class named by "_type" (the wire format stores bare class names, like the
+# reference: torchao/core/config.py:174-305 looks names up in its own ALLOWED_AO_MODULES).  Nothing else is importable.
+ALLOWED_AO_MODULES = (
     "ao_b200.quantization",
     "ao_b200.quantization.granularity",
     "ao_b200.quantization.quant_primitives",
@@ -35,79 +36,60 @@ ALLOWED_AO_MODULES = {
     "ao_b200.quantization.quantize_.workflows",
     "ao_b200.float8.inference",
     "ao_b200.prototype.mx_formats",
-    # names as written by the reference: resolved onto our modules
-    "torchao.quantization",
-    "torchao.prototype.mx_formats",
-    "torchao.float8.inference",
-}
-
-_MODULE_ALIASES = {
-    "torchao.quantization": "ao_b200.quantization",
-    "torchao.prototype.mx_formats": "ao_b200.prototype.mx_formats",
-    "torchao.float8.inference": "ao_b200.float8.inference",
-}
-
-
-def _encode(o: Any) -> Any:
-    if isinstance(o, AOBaseConfig) or (dataclasses.is_dataclass(o) and not isinstance(o, type)):
-        data = {}
-        if dataclasses.is_dataclass(o):
-            for f in dataclasses.fields(o):
-                if f.name == "version":
-                    continue
-                data[f.name] = _encode(getattr(o, f.name))
-        return {"_type": type(o).__name__, "_version": getattr(o, "version", 1), "_data": data,
-                "_module": type(o).__module__}
-    if isinstance(o, tuple) and hasattr(o, "_fields"):  # NamedTuple (e.g. Float8MMConfig)
-        return {"_type": type(o).__name__, "_version": 1, "_data": {k: _encode(v) for k, v in o._asdict().items()},
-                "_module": type(o).__module__}
-    if isinstance(o, enum.Enum):
-        return {"_type": type(o).__name__, "_data": o.name, "_module": type(o).__module__, "_enum": True}
-    if isinstance(o, torch.dtype):
-        return {"_type": "torch.dtype", "_data": str(o).split(".")[-1]}
-    if isinstance(o, (list, tuple)):
-        return [_encode(v) for v in o]
-    if isinstance(o, dict):
-        return {k: _encode(v) for k, v in o.items()}
-    if isinstance(o, torch.Tensor):
-        return {"_type": "torch.Tensor", "_data": o.tolist(), "_dtype": str(o.dtype).split(".")[-1]}
-    return o
+)
 
 
 class ConfigJSONEncoder(json.JSONEncoder):
+    """Same wire format as the reference's encoder (torchao/core/config.py:70-172): configs, NamedTuples and dataclasses
+    become ``{"_type": name, "_version": v, "_data": {...}}`` (configs: every public instance attribute except
+    ``version``), enums ``{"_type": name, "_data": member name}``, dtypes ``{"_type": "torch.dtype", "_data": name}``;
+    plain strings / numbers / None pass through (so a str-Enum field given as a string stays a string)."""
+
     def default(self, o):
-        enc = _encode(o)
-        if enc is o:
-            return super().default(o)
-        return enc
+        if isinstance(o, AOBaseConfig):
+            data = {k: self.encode_value(v) for k, v in o.__dict__.items() if not k.startswith("_") and k != "version"}
+            return {"_type": type(o).__name__, "_version": getattr(o, "version", 1), "_data": data}
+        if isinstance(o, tuple) and hasattr(o, "_fields") and hasattr(o, "_asdict"):  # NamedTuple (Float8MMConfig)
+            return {"_type": type(o).__name__, "_version": getattr(o, "version", 1),
+                    "_data": {k: self.encode_value(v) for k, v in o._asdict().items()}}
+        if dataclasses.is_dataclass(o) and not isinstance(o, type):
+            return {"_type": type(o).__name__, "_version": getattr(o, "version", 1),
+                    "_data": {f.name: self.encode_value(getattr(o, f.name)) for f in dataclasses.fields(o) if f.name != "version"}}
+        if isinstance(o, enum.Enum):
+            return {"_type": type(o).__name__, "_data": o.name}
+        if isinstance(o, torch.dtype):
+            return {"_type": "torch.dtype", "_data": str(o).split(".")[-1]}
+        if isinstance(o, list):
+            return [self.encode_value(v) for v in o]
+        if isinstance(o, tuple):
+            raise NotImplementedError(f"Tuples will be serialized as List in JSON, use Lists instead to avoid surprises. got: {o}")
+        if isinstance(o, dict):
+            return {k: self.encode_value(v) for k, v in o.items()}
+        return super().default(o)
+
+    def encode_value(self, value):
+        try:
+            return self.default(value)
+        except TypeError:
+            return value
 
 
 def config_to_dict(config: AOBaseConfig) -> Dict[str, Any]:
     if not isinstance(config, AOBaseConfig):
         raise TypeError(f"expected an AOBaseConfig, got {type(config)}")
-    return json.loads(json.dumps(_encode(config)))
+    return json.loads(json.dumps(config, cls=ConfigJSONEncoder))
 
 
-def _resolve(module: str, name: str):
-    base = module
-    for allowed in sorted(ALLOWED_AO_MODULES, key=len, reverse=True):
-        if module == allowed or module.startswith(allowed + "."):
-            break
-    else:
-        raise ValueError(f"refusing to import config type {name} from non-allowlisted module {module}")
-    for src, dst in _MODULE_ALIASES.items():
-        if base == src or base.startswith(src + "."):
-            base = dst
-            break
-    for cand in (base, "ao_b200.quantization", "ao_b200.prototype.mx_formats", "ao_b200.float8.inference",
-                 "ao_b200.quantization.quant_primitives", "ao_b200.quantization.quantize_.common"):
+def _resolve(name: str):
+    for modname in ALLOWED_AO_MODULES:
         try:
-            mod = importlib.import_module(cand)
+            mod = importlib.import_module(modname)
         except ImportError:
             continue
-        if hasattr(mod, name):
-            return getattr(mod, name)
-    raise ValueError(f"unknown config type {name} (module {module})")
+        obj = getattr(mod, name, None)
+        if isinstance(obj, type):
+            return obj
+    raise ValueError(f"Failed to find class {name} in any of the allowed modules: {', '.join(ALLOWED_AO_MODULES)}")
 
 
 def _decode(o: Any) -> Any:
@@ -118,10 +100,8 @@ def _decode(o: Any) -> Any:
             t = o["_type"]
             if t == "torch.dtype":
                 return getattr(torch, o["_data"])
-            if t == "torch.Tensor":
-                return torch.tensor(o["_data"], dtype=getattr(torch, o.get("_dtype", "float32")))
-            cls = _resolve(o.get("_module", "ao_b200.quantization"), t)
-            if o.get("_enum") or (isinstance(cls, type) and issubclass(cls, enum.Enum)):
+            cls = _resolve(t)
+            if issubclass(cls, enum.Enum):
                 return cls[o["_data"]]
             kwargs = {k: _decode(v) for k, v in o["_data"].items()}
             version = o.get("_version", None)

@@ -126,8 +126,10 @@ class Int4WeightOnlyConfig(AOBaseConfig):
 
     def __post_init__(self):
         assert self.int4_tile_packed_ntile in [8, 16], "int4_tile_packed_ntile must be either 8 or 16"
-        self.int4_packing_format = Int4PackingFormat(self.int4_packing_format)
-        self.int4_choose_qparams_algorithm = Int4ChooseQParamsAlgorithm(self.int4_choose_qparams_algorithm)
+        # like the reference, the two format fields keep what the caller passed (a plain string stays a string in
+        # the config JSON); both are str-Enums, so comparisons with the enum members work either way
+        Int4PackingFormat(self.int4_packing_format)                      # validates
+        Int4ChooseQParamsAlgorithm(self.int4_choose_qparams_algorithm)   # validates
 
 
 def _int4_weight_only_quantize_tensor(weight, config: Int4WeightOnlyConfig):
@@ -138,11 +140,12 @@ def _int4_weight_only_quantize_tensor(weight, config: Int4WeightOnlyConfig):
                     f"{weight.shape} is not compatible with group_size {group_size}")
         return weight
     block_size = list([1 for _ in range(weight.ndim - 1)] + [group_size])
-    fmt = config.int4_packing_format
+    fmt = Int4PackingFormat(config.int4_packing_format)
     if fmt == Int4PackingFormat.TILE_PACKED_TO_4D:
         assert config.int4_tile_packed_ntile == 8, "ntile 16 is the ROCm variant; CUDA uses 8"
         return Int4TilePackedTo4dTensor.from_hp(weight, block_size,
-                                                int4_choose_qparams_algorithm=config.int4_choose_qparams_algorithm,
+                                                int4_choose_qparams_algorithm=Int4ChooseQParamsAlgorithm(
+                                                    config.int4_choose_qparams_algorithm),
                                                 ntile_size=config.int4_tile_packed_ntile)
     raise NotImplementedError(
         f"int4_packing_format={fmt.value!r}: only 'tile_packed_to_4d' has sm_100a kernels in this engine "

@@ -107,11 +107,45 @@ def test_config_json_roundtrip():
     g = config_from_dict(config_to_dict(f))
     assert list(g.fqn_to_config.keys()) == ["re:.*q_proj", "lm_head", "_default"] and g.fqn_to_config["lm_head"] is None
     with pytest.raises(ValueError):
-        config_from_dict({"_type": "os", "_module": "os", "_data": {}})
+        config_from_dict({"_type": "os", "_data": {}})
+    with pytest.raises(ValueError):
+        config_from_dict({"_type": "Path", "_version": 1, "_data": {}})   # not in the allow-listed modules
     d = config_to_dict(cfgs[0])
     d["_version"] = 99
     with pytest.raises(ValueError):
         config_from_dict(d)
+
+
+def test_config_json_is_the_reference_wire_format():
+    """config_to_dict output == what torchao 0.19 writes for the same configs (fixture made by
+    tests/golden/make_golden_configs.py; this is what HF `TorchAoConfig` stores in config.json), and the reference's
+    dicts load into equal configs."""
+    import json
+
+    from ao_b200.core.config import config_from_dict, config_to_dict
+    from ao_b200.prototype.mx_formats import (MXDynamicActivationMXWeightConfig, NVFP4DynamicActivationNVFP4WeightConfig,
+                                              NVFP4WeightOnlyConfig)
+    from ao_b200.quantization import (Float8DynamicActivationFloat8WeightConfig, FqnToConfig, Int4WeightOnlyConfig,
+                                      Int8DynamicActivationInt8WeightConfig, PerRow)
+
+    with open(os.path.join(ROOT, "tests", "golden", "config_json.json")) as f:
+        gold = json.load(f)
+    cfgs = OrderedDict()
+    cfgs["int4_tile_g32"] = Int4WeightOnlyConfig(group_size=32, int4_packing_format="tile_packed_to_4d")
+    cfgs["int4_tile_g128_hqq"] = Int4WeightOnlyConfig(group_size=128, int4_packing_format="tile_packed_to_4d",
+                                                      int4_choose_qparams_algorithm="hqq")
+    cfgs["int8_dyn"] = Int8DynamicActivationInt8WeightConfig()
+    cfgs["fp8_rowwise"] = Float8DynamicActivationFloat8WeightConfig(granularity=PerRow())
+    cfgs["fp8_default"] = Float8DynamicActivationFloat8WeightConfig()
+    cfgs["mxfp8"] = MXDynamicActivationMXWeightConfig()
+    cfgs["nvfp4_dyn"] = NVFP4DynamicActivationNVFP4WeightConfig()
+    cfgs["nvfp4_wo"] = NVFP4WeightOnlyConfig(use_dynamic_per_tensor_scale=False)
+    cfgs["fqn"] = FqnToConfig(OrderedDict([("re:.*q_proj", cfgs["int4_tile_g32"]), ("lm_head", None),
+                                           ("_default", cfgs["int8_dyn"])]))
+    assert set(gold) == set(cfgs)
+    for name, c in cfgs.items():
+        assert config_to_dict(c) == gold[name], name
+        assert config_from_dict(gold[name]) == c, name
 
 
 def test_handler_registry_and_module_walk():
