@@ -13,6 +13,7 @@
 #include <cuda_fp8.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace ao {
 
@@ -41,6 +42,10 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
                                                             int K, uint8_t* __restrict__ q,
                                                             float* __restrict__ scale) {
   __shared__ float sh[8];
+  // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
+  // be the previous kernel's output, so wait for it before the first read
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
   const int nv = K / 8;
@@ -114,6 +119,10 @@ __device__ __forceinline__ float e8m0_recip(uint8_t e) {
 // one thread per 32-element block
 __global__ void mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
                                    uint8_t* __restrict__ q, uint8_t* __restrict__ sc, int swizzled) {
+  // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
+  // be the previous kernel's output, so wait for it before the first read
+  pdl_launch_dependents();
+  pdl_wait();
   const int nb = K / 32;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)M * nb) return;
@@ -167,6 +176,10 @@ __device__ __forceinline__ uint32_t f32_to_e2m1(float f) {
 __global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
                                    const float* __restrict__ pts, uint8_t* __restrict__ q,
                                    uint8_t* __restrict__ sc, int swizzled) {
+  // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
+  // be the previous kernel's output, so wait for it before the first read
+  pdl_launch_dependents();
+  pdl_wait();
   const int nb = K / 16;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)M * nb) return;
@@ -229,7 +242,7 @@ extern "C" int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t*
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "int8 quantize: null pointer");
   AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<0>, dim3(M), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), false,
+                           reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), K, reinterpret_cast<uint8_t*>(q), scale));
   return AO_OK;
 }
@@ -240,7 +253,7 @@ extern "C" int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t*
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "fp8 quantize: null pointer");
   AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<1>, dim3(M), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), false,
+                           reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), K, q, scale));
   return AO_OK;
 }
@@ -258,7 +271,7 @@ extern "C" int ao_mxfp8_quantize(const uint16_t* x, int M, int K, uint8_t* q, ui
       AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e8m0, bytes));
   }
   const size_t total = (size_t)M * nb;
-  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, false,
+  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), M, K, q, scale_e8m0, swizzled));
   return AO_OK;
 }
@@ -276,7 +289,7 @@ extern "C" int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* p
       AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e4m3, bytes));
   }
   const size_t total = (size_t)M * nb;
-  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, false,
+  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), M, K, per_tensor_scale, q, scale_e4m3, swizzled));
   return AO_OK;
 }
