@@ -5,31 +5,29 @@
 // Used by int4_linear.cu (tinygemm tile-packed int4, W^ = bf16((q-8)s+z)) and
 // nvfp4_weight_linear.cu (e2m1 * e4m3 block scale).  Structure:
 //   * swap-AB: 128 weight rows = UMMA M, tokens = UMMA N (16..128), fp32 accumulator in TMEM
-//   * persistent, one CTA per SM; the (n-tile, 128-k chunk) units of the whole GEMM are split EVENLY
-//     over the CTAs ("stream-K"), so every SM issues the same number of MMAs whatever N/K are
-//   * 16 warps in four warpgroups, 64 registers per thread:
-//       WG0, WG1 (warps 0-7): dequant, alternating chunks: ld.shared (conflict-free through the TMA
-//                  swizzle) -> unpack/scale in bf16x2, one 64-k half row (32 registers) at a time ->
-//                  tcgen05.st of the bf16 A operand into TMEM
-//       WG2 (warps 8-11)             : epilogue: tcgen05.ld of a finished accumulator (double-buffered,
-//                  overlaps the next tile's MMAs), split-tile fix-up through an fp32 workspace, bias, store
-//       WG3 (warp 12 weight TMA producer, warps 13 and 15 MMA issuers, warp 14 activation TMA producer)
-//     One thread can issue a tcgen05.mma only every ~58-70 cycles, and every other memory-pipe operation of
-//     that thread (mbarrier wait, commit) costs it another 100-300 cycles (scripts/mma_microbench*.cu), so the
-//     issuer's loop is stripped to ONE wait and ONE commit per chunk: the activation slot of a chunk shares the
-//     index and the barriers of the chunk's TMEM A stage (afull[t] = 4 dequant arrivals + the activation
-//     tile's transaction bytes; one tcgen05.commit on aempty[t] frees both), and for UMMA N <= 32 there are TWO
-//     issuers (issue rate scales linearly with issuing warps): even chunks go to issuer 0, odd chunks to
-//     issuer 1, each into its own TMEM accumulator; the epilogue adds the two in a fixed order, so results
-//     stay bit-reproducible.
-//     64 registers/thread at launch + 256 TMEM columns + ~105 KB smem => two CTAs fit on an SM.  The grid is
-//     two CTAs per SM: per-thread costs (MMA issue, TMA issue, barrier round trips) are what bound one CTA,
-//     so two independent CTAs per SM double the streaming rate, and a finishing CTA's slot is refilled by the
-//     next linear's CTA (PDL) which prefetches weights while its neighbour drains
-//   * tiles split across CTAs are reduced deterministically: every CTA writes its partial, bumps the
-//     tile's unit counter, and whoever completes the count sums the partials in CTA order
-//   * PDL: griddepcontrol.launch_dependents at start; weights are prefetched before
-//     griddepcontrol.wait, only activations / outputs / workspace wait for the previous kernel.
+//   * persistent stream-K: the (n-tile, 128-k chunk) units of the whole GEMM are split EVENLY over the CTAs, so every
+//     SM streams the same number of bytes whatever N/K are.  Grid (launchers): two CTAs per SM when a CTA would get
+//     fewer than 16 chunks, else one (room for the next linear's CTA to become resident under this one, PDL)
+//   * 16 warps in four warpgroups, 64 registers per thread, 256 TMEM columns, ~105 KB smem (two CTAs fit per SM):
+//       WG0, WG1 (warps 0-7): dequant, alternating chunks: ld.shared (conflict-free through the TMA swizzle) ->
+//                  unpack/scale in bf16x2, one 64-k half row (32 registers) at a time -> tcgen05.st of the bf16
+//                  A operand into one of 3 TMEM A stages
+//       WG2 (warps 8-11): epilogue: tcgen05.ld of a finished accumulator (double-buffered in TMEM: overlaps the
+//                  next tile's MMAs), split-tile reduction through an fp32 workspace, bias, store
+//       WG3: warp 12 weight TMA producer (never waits for the previous kernel), warp 14 activation TMA producer
+//                  (after griddepcontrol.wait), warp 13 MMA issuer (warp 15: second issuer when Cfg::NI == 2)
+//   * single-thread roles are WARP-UNIFORM loops with only the tcgen05 / TMA / mbarrier instruction under elect.sync
+//     (warp index through __shfl_sync so the compiler knows it is uniform): with a loop under `lane == 0` ptxas wraps
+//     every UTCHMMA / UTMALDG in an elect-broadcast loop and one thread issues an MMA only every ~52 cycles instead
+//     of ~20, the tensor pipe's own floor for M128 N16 K16 (scripts/mma_microbench7.cu)
+//   * the issuer does ONE wait and ONE commit per chunk: the activation slot of a chunk shares the index and the
+//     barriers of the chunk's TMEM A stage (afull = 4 dequant-warp arrivals + the activation tile's TMA transaction
+//     bytes; one tcgen05.commit on aempty frees both).  A-stage barriers are PAIRS per stage (see below)
+//   * tiles split across CTAs are reduced deterministically: every CTA writes its partial, bumps the tile's unit
+//     counter, and whoever completes the count sums the partials in CTA order (bit-reproducible run to run); the
+//     CTA's LAST such reduction is on the kernel's critical path and is shared by all four warpgroups
+//   * PDL: griddepcontrol.launch_dependents at start; only activations / outputs / workspace wait
+//     (griddepcontrol.wait) for the previous kernel.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -47,7 +45,6 @@ constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage 
 constexpr int DEQ_WARPS = 8, EPI_WARP0 = 8, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14, MMA_WARP1 = 15;
 constexpr int WSTAGE_BYTES = W_BYTES + AUX_BYTES;  // one weight stage: packed nibbles + scales
 constexpr int NUM_THREADS = 16 * 32;
-constexpr int REGS_DEQ = 96, REGS_OTHER = 32;
 
 // DBUF = accumulator buffers per issuer (2: the epilogue of a tile overlaps the next tile's MMAs)
 template <int N_MMA, int DBUF = 2>
@@ -101,11 +98,6 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
-
-template <int R>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 // the eight K=16 MMAs of one 128-k chunk in one straight-line block: A stage at TMEM column a0 (8 columns per
 // MMA), B = two 64-k swizzle atoms (descriptors b_lo / b_hi, +32 B = +2 in the address field per MMA)
