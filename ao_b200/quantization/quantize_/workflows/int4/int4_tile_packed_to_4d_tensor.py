@@ -13,6 +13,7 @@ from __future__ import annotations
 from typing import List, Optional
 
 import torch
+from torch.utils._python_dispatch import return_and_correct_aliasing
 
 from ao_b200.quantization.quant_primitives import choose_qparams_affine_tinygemm, quantize_affine_tinygemm
 from ao_b200.quantization.utils import pack_tinygemm_scales_and_zeros
@@ -58,7 +59,10 @@ class Int4TilePackedTo4dTensor(TorchAOBaseTensor):
         assert hp_tensor.dtype == torch.bfloat16, f"Only bfloat16 is supported for Int4TilePackedTo4dTensor, got {hp_tensor.dtype}"
         assert hp_tensor.dim() == 2, "Int4TilePackedTo4dTensor: 2-D weights only"
         if not hp_tensor.is_cuda:
-            raise ValueError("Int4TilePackedTo4dTensor.from_hp needs a CUDA tensor (the packing kernel is sm_100a CUDA)")
+            # same exception type as the reference, where aten::_convert_weight_to_int4pack has no CPU kernel
+            # (test_int4_tile_packed_to_4d_tensor.py:194-202)
+            raise NotImplementedError("Could not run 'ao_b200::int4_pack_tile4d' with arguments from the 'CPU' backend: "
+                                      "Int4TilePackedTo4dTensor.from_hp needs a CUDA tensor (sm_100a packing kernel)")
         original_shape = hp_tensor.shape
         N0, K0 = original_shape
         g = block_size[-1]
@@ -140,7 +144,10 @@ def _(func, types, args, kwargs):
         qd = self.qdata[:, start // 128: end // 128]
         sz = self.scale_and_zero[start // g: end // g]
         shape = torch.Size([N, end - start])
-    return Int4TilePackedTo4dTensor(qd.contiguous(), sz.contiguous(), self.block_size, shape, self.act_pre_scale)
+    # views, like the reference (:302-360): `param.data.narrow(...).copy_(loaded.narrow(...))` must write through to the
+    # parameter's own storage; callers that run a linear on a slice make it contiguous first (the handler asserts it)
+    return return_and_correct_aliasing(
+        func, args, kwargs, Int4TilePackedTo4dTensor(qd, sz, self.block_size, shape, self.act_pre_scale))
 
 
 Int4TilePackedTo4dTensor.__module__ = "ao_b200.quantization"

@@ -265,3 +265,107 @@ def test_ops_pass_opcheck_and_survive_fullgraph_tracing():
     compiled = torch.compile(lin, fullgraph=True, backend="aot_eager")
     y_comp = compiled(x)
     assert torch.equal(y_eager, y_comp)
+
+
+# ------------------------------------------------------------------ the reference's own tensor-level tests
+# (test/quantization/quantize_/workflows/int4/test_int4_tile_packed_to_4d_tensor.py), restated for this package
+def _int4_cfg(algo="tinygemm", g=128):
+    from ao_b200.quantization import Int4WeightOnlyConfig
+
+    return Int4WeightOnlyConfig(group_size=g, int4_packing_format="tile_packed_to_4d", int4_choose_qparams_algorithm=algo)
+
+
+def _sqnr(a, b):
+    return (20 * torch.log10(a.float().norm() / (a.float() - b.float()).norm())).item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["tinygemm", "hqq"])
+def test_reference_slice_semantics(algo):
+    """reference :90-192: narrow on dim 0 / dim 1 equals narrowing the packed payloads, keeps aliasing, and a linear on
+    the (contiguous) slice matches the bf16 linear on the sliced weight (SQNR > 14 dB at g=128)."""
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import quantize_
+
+    torch.manual_seed(0)
+    dummy = torch.nn.Linear(2048, 2048, bias=False, dtype=torch.bfloat16, device="cuda")
+    w_hp = dummy.weight.detach().clone()
+    quantize_(dummy, _int4_cfg(algo))
+    w = dummy.weight
+    w1 = w.narrow(0, 0, 1024)
+    assert torch.equal(w1.qdata, w.qdata.narrow(0, 0, 128)) and torch.equal(w1.scale_and_zero, w.scale_and_zero.narrow(1, 0, 1024))
+    assert w1.qdata.data_ptr() == w.qdata.data_ptr() and w1.scale_and_zero.data_ptr() == w.scale_and_zero.data_ptr()
+    w2 = w.narrow(1, 0, 1024)
+    assert torch.equal(w2.qdata, w.qdata.narrow(1, 0, 8)) and torch.equal(w2.scale_and_zero, w.scale_and_zero.narrow(0, 0, 8))
+    x1 = torch.randn(2, 2048, dtype=torch.bfloat16, device="cuda")
+    l1 = torch.nn.Linear(2048, 1024, bias=False, dtype=torch.bfloat16, device="cuda")
+    l1.weight = torch.nn.Parameter(w1.contiguous(), requires_grad=False)
+    assert _sqnr(x1 @ w_hp[:1024].t(), l1(x1)) > 14
+    x2 = torch.randn(2, 1024, dtype=torch.bfloat16, device="cuda")
+    l2 = torch.nn.Linear(1024, 2048, bias=False, dtype=torch.bfloat16, device="cuda")
+    l2.weight = torch.nn.Parameter(w2.contiguous(), requires_grad=False)
+    assert _sqnr(x2 @ w_hp[:, :1024].t(), l2(x2)) > 14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["tinygemm", "hqq"])
+def test_reference_slice_and_copy_similar_to_vllm(algo):
+    """reference torchao/testing/utils.py:471-519 (vLLM's weight loader), plus the write-through the loader relies on."""
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import quantize_
+
+    torch.manual_seed(1)
+    dst_l = torch.nn.Linear(1024, 1024, device="cuda", dtype=torch.bfloat16)
+    quantize_(dst_l, _int4_cfg(algo))
+    src_l = torch.nn.Linear(1024, 1024, device="cuda", dtype=torch.bfloat16)
+    src_l.weight = torch.nn.Parameter(src_l.weight + 1.0 + 2 * torch.randn(1024, 1024, device="cuda", dtype=torch.bfloat16),
+                                      requires_grad=False)
+    quantize_(src_l, _int4_cfg(algo))
+    for rank in (0, 1):
+        pd = dst_l.weight.data.narrow(0, rank * 512, 512)
+        lw = src_l.weight.narrow(0, rank * 512, 512)
+        assert not torch.equal(pd.qdata[0], lw.qdata[0])
+        pd.copy_(lw)
+        assert torch.equal(pd.qdata[0], lw.qdata[0]) and torch.equal(pd.scale_and_zero, lw.scale_and_zero)
+    assert torch.equal(dst_l.weight.qdata, src_l.weight.qdata) and torch.equal(dst_l.weight.scale_and_zero, src_l.weight.scale_and_zero)
+
+
+@pytest.mark.gpu
+def test_reference_module_path_prescale_to_device_and_cpu_error():
+    """reference :72-88 (type path survives state_dict save/load), :242-260 (act_pre_scale), :204-220 (.to(device)),
+    :194-202 (CPU init raises NotImplementedError), :298-308 (group sizes 32/64/128)."""
+    import io
+
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import quantize_
+
+    lin = torch.nn.Linear(128, 256, dtype=torch.bfloat16, device="cuda")
+    quantize_(lin, _int4_cfg())
+    assert str(type(lin.weight)) == "<class 'ao_b200.quantization.Int4TilePackedTo4dTensor'>"
+    buf = io.BytesIO()
+    torch.save(lin.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf, weights_only=True)
+    assert str(type(sd["weight"])) == "<class 'ao_b200.quantization.Int4TilePackedTo4dTensor'>"
+    assert torch.equal(sd["weight"].qdata, lin.weight.qdata)
+    lin.to("cuda")
+    lin.to(device="cuda")
+
+    x = torch.randn(1, 128, dtype=torch.bfloat16, device="cuda")
+    l2 = torch.nn.Linear(128, 256, bias=False, dtype=torch.bfloat16, device="cuda")
+    original = l2(x)
+    quantize_(l2, _int4_cfg())
+    assert l2.weight.act_pre_scale is None
+    l2.weight.act_pre_scale = 2
+    assert _sqnr(original * 2, l2(x)) > 20
+
+    with pytest.raises(NotImplementedError):
+        quantize_(torch.nn.Linear(128, 256, dtype=torch.bfloat16), _int4_cfg())
+
+    for g in (32, 64, 128):
+        l3 = torch.nn.Linear(1024, 512, bias=False, dtype=torch.bfloat16, device="cuda")
+        ref = l3.weight.detach().clone()
+        quantize_(l3, _int4_cfg(g=g))
+        assert l3.weight.block_size == [1, g]
+        xx = torch.randn(4, 1024, dtype=torch.bfloat16, device="cuda")
+        assert _sqnr(xx @ ref.t(), l3(xx)) > 20

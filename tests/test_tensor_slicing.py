@@ -82,3 +82,34 @@ def test_narrow_copy_loader_pattern(gold):
     assert torch.equal(t8.narrow(1, 0, 64).qdata, q[:, :64]) and t8.narrow(1, 0, 64).scale.shape == (64, 1)
     f8 = Float8Tensor(q.view(torch.float8_e4m3fn) if False else torch.zeros(64, 128).to(torch.float8_e4m3fn), torch.rand(64, 1), [1, 128])
     assert f8.narrow(0, 0, 16).scale.shape == (16, 1)
+
+
+def test_int4_narrow_copy_writes_through_to_the_parameter():
+    """vLLM's loader (reference torchao/testing/utils.py:471-519): narrow both sides, copy_ in place.  The narrowed
+    tensor must alias the parameter's storage for BOTH payload tensors, otherwise the loaded shard is lost."""
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import Int4TilePackedTo4dTensor
+
+    N, K, g = 1024, 1024, 32
+
+    def make(seed):
+        gen = torch.Generator().manual_seed(seed)
+        return Int4TilePackedTo4dTensor(torch.randint(-2**31, 2**31 - 1, (N // 8, K // 128, 32, 4), dtype=torch.int32, generator=gen),
+                                        torch.rand(K // g, N, 2, generator=gen).to(torch.bfloat16), [1, g], [N, K])
+
+    param, loaded = make(0), make(1)
+    for rank in (0, 1):
+        dst = param.narrow(0, rank * 512, 512)
+        src = loaded.narrow(0, rank * 512, 512)
+        assert dst.qdata.data_ptr() == param.qdata[rank * 64:].data_ptr()      # aliasing (reference test_slice_preserves_aliasing)
+        assert not torch.equal(dst.qdata[0], src.qdata[0])
+        dst.copy_(src)
+        assert torch.equal(dst.qdata, src.qdata) and torch.equal(dst.scale_and_zero, src.scale_and_zero)
+    assert torch.equal(param.qdata, loaded.qdata) and torch.equal(param.scale_and_zero, loaded.scale_and_zero)
+    # K-dim narrow (row-parallel layers): multiples of 1024 only
+    half = make(2)
+    big = Int4TilePackedTo4dTensor(torch.zeros(N // 8, 2 * K // 128, 32, 4, dtype=torch.int32),
+                                   torch.zeros(2 * K // g, N, 2, dtype=torch.bfloat16), [1, g], [N, 2 * K])
+    big.narrow(1, K, K).copy_(half)
+    assert torch.equal(big.qdata[:, K // 128:], half.qdata) and torch.equal(big.scale_and_zero[K // g:], half.scale_and_zero)
+    assert int(big.qdata[:, : K // 128].abs().sum()) == 0
