@@ -221,7 +221,7 @@ def test_int4_skip_rule_and_unsupported_formats():
     lin = torch.nn.Linear(128, 16, bias=False, dtype=torch.bfloat16)
     with pytest.raises(NotImplementedError):
         quantize_(lin, Int4WeightOnlyConfig(group_size=32))
-    with pytest.raises(ValueError):  # CPU tensor: the packer is CUDA-only, like the reference (:124)
+    with pytest.raises(NotImplementedError):  # CPU tensor: no CPU packing kernel; same exception type as the reference
         quantize_(lin, Int4WeightOnlyConfig(group_size=32, int4_packing_format="tile_packed_to_4d"))
     lin32 = torch.nn.Linear(128, 16, bias=False, dtype=torch.float32)
     with pytest.raises(AssertionError):
