@@ -113,3 +113,30 @@ def test_int4_narrow_copy_writes_through_to_the_parameter():
     big.narrow(1, K, K).copy_(half)
     assert torch.equal(big.qdata[:, K // 128:], half.qdata) and torch.equal(big.scale_and_zero[K // g:], half.scale_and_zero)
     assert int(big.qdata[:, : K // 128].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("kind", ["int8", "fp8"])
+def test_rowwise_classes_narrow_copy_aliasing(kind):
+    """reference test_float8_tensor.py::test_slice_preserves_aliasing / test_slice_and_copy_similar_to_vllm and the int8
+    equivalents: narrow returns views of qdata and of the per-row scale; copy_ through them updates the parameter."""
+    import ao_b200  # noqa: F401
+    from ao_b200.quantization import Float8Tensor, Int8Tensor
+
+    def make(seed):
+        gen = torch.Generator().manual_seed(seed)
+        if kind == "int8":
+            return Int8Tensor(torch.randint(-128, 127, (1024, 512), dtype=torch.int8, generator=gen),
+                              torch.rand(1024, 1, generator=gen), [1, 512], torch.bfloat16)
+        return Float8Tensor(torch.randn(1024, 512, generator=gen).to(torch.float8_e4m3fn), torch.rand(1024, 1, generator=gen), [1, 512])
+
+    param, loaded = make(0), make(1)
+    view = param.narrow(0, 0, 512)
+    assert view.qdata.data_ptr() == param.qdata.data_ptr() and view.scale.data_ptr() == param.scale.data_ptr()
+    for rank in (0, 1):
+        dst, src = param.narrow(0, rank * 512, 512), loaded.narrow(0, rank * 512, 512)
+        dst.copy_(src)
+        assert torch.equal(dst.qdata.view(torch.uint8), src.qdata.view(torch.uint8)) and torch.equal(dst.scale, src.scale)
+    assert torch.equal(param.qdata.view(torch.uint8), loaded.qdata.view(torch.uint8)) and torch.equal(param.scale, loaded.scale)
+    cols = param.narrow(1, 0, 256)      # K-dim narrow of a rowwise tensor keeps the whole scale column
+    assert cols.qdata.shape == (1024, 256) and cols.scale.shape == (1024, 1)
+    assert cols.scale.data_ptr() == param.scale.data_ptr()
