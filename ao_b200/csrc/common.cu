@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
 
 namespace ao {
 
@@ -60,6 +62,19 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void*
                 (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0,
                 rank > 2 ? box[2] : 0);
   return AO_OK;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.insert({kernel, dev});
+  return e;
 }
 
 bool pdl_enabled() {

@@ -63,6 +63,9 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device).
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // PDL can be disabled globally (AO_B200_NO_PDL=1) for debugging.
 bool pdl_enabled();
 // AO_B200_TIMELINE=1: kernels record per-CTA phase timestamps at workspace + 48 KiB (bring-up only).

@@ -200,11 +200,7 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
     return fail(AO_ERR_WORKSPACE, "int4 linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true, DBUF>
                                            : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false, DBUF>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[p.timeline ? 1 : 0]) {
-    AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set[p.timeline ? 1 : 0] = true;
-  }
+  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_sz,
                        tm_x, p));
   return AO_OK;

@@ -432,11 +432,7 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)
     return fail(AO_ERR_WORKSPACE, "lowp linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = lowp_linear_kernel<KIND, N_MMA>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
-  }
+  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   AO_CUDA_CHECK(ao::launch(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_x,
                            w_sf, x_sf, p));
   return AO_OK;

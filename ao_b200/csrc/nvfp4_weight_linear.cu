@@ -122,11 +122,7 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)
     return fail(AO_ERR_WORKSPACE, "nvfp4 weight linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, N_MMA>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
-  }
+  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
   return AO_OK;
 }
