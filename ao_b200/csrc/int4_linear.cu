@@ -48,6 +48,12 @@ struct Int4Fmt {
     tma_load_3d(w_dst, tm_w, bar, 0, 4 * kc, n_tile * (ROWS / 8), policy);
     tma_load_2d(aux_dst, tm_sz, bar, n_tile * ROWS, (kc * KCHUNK) / p.group_size, policy);
   }
+  // HBM -> L2 of the same two boxes (no shared memory): issued `prefetch` chunks ahead of the ring
+  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap* tm_sz,
+                                                    const tsg::Params& p, int n_tile, int kc) {
+    tma_prefetch_l2_3d(tm_w, 0, 4 * kc, n_tile * (ROWS / 8));
+    tma_prefetch_l2_2d(tm_sz, n_tile * ROWS, (kc * KCHUNK) / p.group_size);
+  }
   // thread r (= TMEM lane = weight row of the tile), k-half h: 32 packed bytes + up to 2 (s,z) pairs -> 32 bf16x2
   // (out[c] = k pair 64h + 2c, 64h + 2c + 1).  The row's 64 bytes are four 16-byte lane words (tinygemm word
   // wd = k 32wd..32wd+31 sits at byte 4wd of each); half h needs words 2h, 2h+1 = the 8 bytes at +8h of each.
@@ -97,7 +103,7 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
                                           const __nv_bfloat16* __restrict__ sz,
                                           const __nv_bfloat16* __restrict__ bias,
                                           __nv_bfloat16* __restrict__ y, int M, int N, int N_out,
-                                          int K, int g) {
+                                          int K, int g, int ldx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   const int m0 = blockIdx.y * MT;
@@ -124,7 +130,7 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
             const float wf = __bfloat162float(wv);
 #pragma unroll
             for (int m = 0; m < MT; ++m)
-              if (m0 + m < M) acc[m] += __bfloat162float(x[(size_t)(m0 + m) * K + k]) * wf;
+              if (m0 + m < M) acc[m] += __bfloat162float(x[(size_t)(m0 + m) * ldx + k]) * wf;
           }
         }
       }
@@ -141,7 +147,7 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
 
 
 template <int N_MMA, int DBUF = 2>
-static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
+static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
                      const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes,
                      cudaStream_t stream) {
   using C = tsg::Cfg<N_MMA, DBUF>;
@@ -164,7 +170,7 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint64_t str[1] = {(uint64_t)ldx * 2};
     const uint32_t box[2] = {64, (uint32_t)N_MMA};
     int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -172,32 +178,17 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
   tsg::Params p{};
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  p.ws_sem = reinterpret_cast<unsigned int*>(ws);
-  p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 64 * 1024);
   p.M = M; p.N = N; p.N_out = N_out; p.K = K; p.group_size = g;
   p.n_tiles = ceil_div(N_out, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);
   p.KT = KT;
-  p.flags = ts_flags();
-  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 8 stamps + 4 x 8 fine stamps
+  int grid = 0;
+  if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
+  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 8 stamps
   static unsigned tl_launch = 0;
-  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024 +
-                                                                         (size_t)(tl_launch++ & 1) * (100 * 8 + 32) * 8)
+  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_TIMELINE_OFF +
+                                                                         (size_t)(tl_launch++ & 1) * (100 * 8) * 8)
                                   : nullptr;
-  const long long units = (long long)p.n_tiles * p.m_blocks * KT;
-  // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  // two CTAs per SM (twice the warps hiding the per-chunk latencies) when a CTA would otherwise get fewer than
-  // 16 chunks; with longer ranges one CTA per SM leaves room for the next linear's CTA to become resident and
-  // prefetch its weights under this one (PDL), which is worth more
-  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : (units < 16LL * sm_count() ? 2 : 1);
-  int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
-  // small problems: at least 4 (decode, one token column to reduce) or 8 chunks per CTA: splitting a tile over
-  // more CTAs shortens the streaming phase but lengthens the split-tile reduction, a chain of L2 round trips
-  const int min_units = ts_min_units() ? ts_min_units() : (M <= 8 ? 4 : 8);
-  if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
-  const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
-  if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)
-    return fail(AO_ERR_WORKSPACE, "int4 linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true, DBUF>
                                            : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false, DBUF>;
   AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
@@ -209,11 +200,11 @@ static int launch_tc(const uint16_t* x, int M, int K, const int32_t* qdata, cons
 }  // namespace int4k
 }  // namespace ao
 
-extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qdata,
-                                         const uint16_t* scale_and_zero, int group_size, int N,
-                                         const uint16_t* bias, uint16_t* y, int N_out,
-                                         void* workspace, size_t workspace_bytes, int impl,
-                                         void* stream) {
+extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
+                                                 const uint16_t* scale_and_zero, int group_size, int N,
+                                                 const uint16_t* bias, uint16_t* y, int N_out,
+                                                 void* workspace, size_t workspace_bytes, int impl,
+                                                 void* stream) {
   using namespace ao;
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "int4 linear: bad sizes M=%d K=%d N=%d", M, K, N);
   AO_REQUIRE(K % 1024 == 0, "int4 linear: K=%d must be a multiple of 1024 (format pads K)", K);
@@ -221,8 +212,10 @@ extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const 
   AO_REQUIRE(N_out > 0 && N_out <= N, "int4 linear: N_out=%d out of range (N=%d)", N_out, N);
   AO_REQUIRE(group_size == 32 || group_size == 64 || group_size == 128 || group_size == 256,
              "int4 linear: group_size=%d not in {32,64,128,256}", group_size);
+  AO_REQUIRE(ldx >= K && ldx % 8 == 0, "int4 linear: ldx=%d must be >= K=%d and a multiple of 8", ldx, K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && qdata && scale_and_zero && y, "int4 linear: null pointer");
+  AO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "int4 linear: x must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (impl == 2) {
     constexpr int MT = 8;
@@ -231,23 +224,27 @@ extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const 
                          reinterpret_cast<const __nv_bfloat16*>(x), qdata,
                          reinterpret_cast<const __nv_bfloat16*>(scale_and_zero),
                          reinterpret_cast<const __nv_bfloat16*>(bias),
-                         reinterpret_cast<__nv_bfloat16*>(y), M, N, N_out, K, group_size));
+                         reinterpret_cast<__nv_bfloat16*>(y), M, N, N_out, K, group_size, ldx));
     return AO_OK;
   }
   if (M <= 16)
-    return int4k::launch_tc<16>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+    return int4k::launch_tc<16>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
-  if (M <= 32) {
-    // bring-up switch: AO_B200_TS_FLAGS & 16 = single-buffered accumulators (3 A stages instead of 2)
-    if (ts_flags() & 16)
-      return int4k::launch_tc<32, 1>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                     workspace_bytes, st);
-    return int4k::launch_tc<32>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+  if (M <= 32)
+    return int4k::launch_tc<32>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
-  }
   if (M <= 64)
-    return int4k::launch_tc<64>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+    return int4k::launch_tc<64>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
-  return int4k::launch_tc<128>(x, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+  return int4k::launch_tc<128>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                workspace_bytes, st);
+}
+
+extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qdata,
+                                         const uint16_t* scale_and_zero, int group_size, int N,
+                                         const uint16_t* bias, uint16_t* y, int N_out,
+                                         void* workspace, size_t workspace_bytes, int impl,
+                                         void* stream) {
+  return ao_int4_tilepacked_linear_strided(x, K, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+                                           workspace_bytes, impl, stream);
 }

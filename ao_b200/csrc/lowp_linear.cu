@@ -11,20 +11,23 @@
 // operand (N_MMA tokens).  TMA (SWIZZLE_128B) streams 128-byte-wide K blocks of W through a
 // deep smem ring straight into tcgen05.mma (SS mode) -- no register staging at all; block
 // scales go smem -> TMEM with tcgen05.cp.  Epilogue: TMEM -> registers -> scale/bias -> bf16.
-// Persistent: one CTA per SM, (tile, K-chunk) units split evenly over the CTAs (stream-K); tiles shared by
-// several CTAs are reduced deterministically through a 32-bit workspace (int32 for int8: stays exact).
+// Persistent stream-K (streamk.cuh): (tile, K-chunk) units split evenly over the CTAs; tiles shared by several
+// CTAs are finished by their owner CTA from the contributors' published 32-bit partials in CTA order
+// (deterministic; int32 for int8: stays exact).  The TMA producer also runs an L2 prefetch of the weight
+// chunks ahead of the shared-memory ring (the weight stream depends on nothing).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
+#include "streamk.cuh"
 
 namespace ao {
 namespace lowp {
 
 enum Kind { KIND_I8 = 0, KIND_F8 = 1, KIND_MXF8 = 2, KIND_NVF4 = 3 };
 
-constexpr int ROWS = 128;
+using streamk::ROWS;
 constexpr int KB = 128;             // bytes of K per stage per row (128 elems for 8-bit, 256 for fp4)
 constexpr int A_BYTES = ROWS * KB;  // 16 KiB
 constexpr int EPI_WARP0 = 0, TMA_WARP = 4, MMA_WARP = 5;
@@ -56,18 +59,17 @@ struct Params {
   const __nv_bfloat16* bias;
   __nv_bfloat16* y;       // bf16 out [M, N]  (null when i32_out is set)
   int32_t* i32_out;       // raw int32 accumulators [M, N] (ao_int8_mm_i32)
-  float* ws_partial;      // [grid][2][N_MMA*128] 32-bit partials (int32 bits for int8)
-  unsigned int* ws_sem;   // [tiles]
+  float* ws_partial;      // [grid][N_MMA*128] 32-bit partials (int32 bits for int8): CTA b's CONTRIB partial
+  unsigned int* ws_flag;  // [grid] CTA b's partial is published (streamk.cuh)
+  int prefetch;           // weight chunks of L2 prefetch ahead of the ring (0 = none)
   int M, N, K;            // K in ELEMENTS
   int n_tiles, m_blocks, KT;  // KT = chunks of 128 K-bytes
   int sf_col_blocks_w;    // number of 4-wide scale column blocks per row block (blocked layout)
   int sf_col_blocks_x;
 };
 
-__device__ __forceinline__ int unit_begin(int b, long long U, int G) { return (int)((U * b) / G); }
-__device__ __forceinline__ int cta_of_unit(int u, long long U, int G) {
-  return (int)((((long long)(u + 1)) * G + U - 1) / U) - 1;
-}
+using streamk::cta_of_unit;
+using streamk::unit_begin;
 
 // Persistent stream-K kernel (same work split / fix-up protocol as ts_gemm.cuh, SS-mode MMAs):
 // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.
@@ -87,7 +89,6 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   uint64_t* dfull = sempty + S;      // [2]
   uint64_t* dempty = dfull + 2;      // [2] 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
-  uint32_t* flag_slot = tmem_slot + 1;
 
   // warp index through a shuffle => known warp-uniform: the single-thread roles are warp-uniform loops with only
   // the TMA / tcgen05 instructions under elect.sync, so their operands live in uniform registers (with the whole
@@ -97,6 +98,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
   const int u0 = unit_begin(b, U, G), u1 = unit_begin(b + 1, U, G);
   const int nunits = u1 - u0;
+  const streamk::Walk walk(u0, nunits, p.KT);
   auto tile_of = [&](int i) { return (u0 + i) / p.KT; };
   auto kc_of = [&](int i) { return (u0 + i) % p.KT; };
 
@@ -156,11 +158,28 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               : "memory");
         }
       };
+      auto prefetch_w = [&](int i) {
+        const int n_tile = tile_of(i) % p.n_tiles, kc = kc_of(i);
+        tma_prefetch_l2_2d(&tm_w, kc * KB, n_tile * ROWS);
+        if (C::BLOCK_SCALED)
+          bulk_prefetch_l2(w_sf + ((size_t)n_tile * p.sf_col_blocks_w + (size_t)kc * C::SF_TILES) * 512, C::SF_BYTES);
+      };
       const int pre = nunits < S ? nunits : S;
       for (int i = 0; i < pre; ++i) {
         if (elect_one()) issue_w(i);   // weights never depend on the previous kernel
         __syncwarp();
       }
+      // HBM -> L2 of the chunks behind the first ring-full (no shared memory needed): under PDL this runs while the
+      // previous kernel is still finishing
+      int pf = pre;
+      auto prefetch_to = [&](int upto) {
+        if (upto > nunits) upto = nunits;
+        for (; pf < upto; ++pf) {
+          if (elect_one()) prefetch_w(pf);
+          __syncwarp();
+        }
+      };
+      if (p.prefetch > 0) prefetch_to(pre + p.prefetch);
       pdl_wait();
       for (int i = 0; i < pre; ++i) {
         if (elect_one()) issue_x(i);
@@ -173,6 +192,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           issue_x(i);
         }
         __syncwarp();
+        if (p.prefetch > 0) prefetch_to(i + 1 + p.prefetch);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -238,11 +258,9 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     const int r = q4 * 32 + lane;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     pdl_wait();
-    int seg = 0, i = 0;
-    while (i < nunits) {
-      const int tile = tile_of(i);
-      int cnt = p.KT - kc_of(i);
-      if (cnt > nunits - i) cnt = nunits - i;
+    for (int seg = 0; seg < walk.nseg; ++seg) {
+      const int tile = walk.seg_tile(seg);
+      const int kind = walk.seg_kind(seg);
       const int buf = seg & 1;
       mbar_wait(&dfull[buf], (seg >> 1) & 1);
       tc_fence_after();
@@ -273,7 +291,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(raw_f * sw + bias);
         }
       };
-      if (cnt == p.KT) {
+      if (kind == streamk::SEG_FULL) {
 #pragma unroll
         for (int j = 0; j < N_MMA; j += 16) {
           uint32_t rr[16];
@@ -285,12 +303,9 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               if (m0 + j + q < p.M) emit(m0 + j + q, rr[q], __uint_as_float(rr[q]));
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dempty[buf]);
-      } else {
-        const int which = (u0 / p.KT == tile) ? 0 : 1;
-        uint32_t* slot = reinterpret_cast<uint32_t*>(p.ws_partial) + ((size_t)b * 2 + which) * (N_MMA * ROWS);
+      } else if (kind == streamk::SEG_CONTRIB) {
+        // publish the partial (column-major slot: coalesced across the 128 rows), then raise this CTA's flag
+        uint32_t* slot = reinterpret_cast<uint32_t*>(p.ws_partial) + (size_t)b * (N_MMA * ROWS) + r;
 #pragma unroll
         for (int j = 0; j < N_MMA; j += 16) {
           uint32_t rr[16];
@@ -298,83 +313,66 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           tc_wait_ld();
 #pragma unroll
           for (int q = 0; q < 16; ++q)
-            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS + r], rr[q]);
+            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS], rr[q]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dempty[buf]);
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == EPI_WARP0 * 32) {
-          const unsigned prev = atomicAdd(&p.ws_sem[tile], (unsigned)cnt);
-          *flag_slot = (prev + (unsigned)cnt == (unsigned)p.KT) ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool finish = (*flag_slot != 0);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (finish) {
-          __threadfence();
-          const int b_first = cta_of_unit(tile * p.KT, U, G);
-          const int b_last = cta_of_unit(tile * p.KT + p.KT - 1, U, G);
-          const bool first_is_tail = unit_begin(b_first, U, G) < tile * p.KT;
-          if (threadIdx.x == EPI_WARP0 * 32) p.ws_sem[tile] = 0;
-          if (n < p.N) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // all 128 rows stored (cta-scope order) ...
+        if (threadIdx.x == EPI_WARP0 * 32) streamk::st_release_u32(p.ws_flag + b, 1u);   // ... one gpu-scope release
+      } else {
+        // OWNER: own partial (TMEM) + the partials of CTAs b+1 .. b_last in that order (fixed: deterministic)
+        const int b_last = cta_of_unit((long long)tile * p.KT + p.KT - 1, U, G);
+        const int n_oth = b_last - b;
+        const uint32_t* slot0 = reinterpret_cast<const uint32_t*>(p.ws_partial) + (size_t)(b + 1) * (N_MMA * ROWS) + r;
+        streamk::wait_flags(p.ws_flag + b + 1, n_oth, lane);
 #pragma unroll 1
-            for (int j0 = 0; j0 < N_MMA; j0 += 16) {
-              if (m0 + j0 >= p.M) break;
-              float vf[16];
-              int32_t vi[16];
+        for (int j0 = 0; j0 < N_MMA; j0 += 16) {
+          if (m0 + j0 >= p.M) break;
+          uint32_t own[16];
+          tmem_ld_x16(d_t + j0, own);
+          tc_wait_ld();
+          float vf[16];
+          int32_t vi[16];
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                vf[q] = 0.f;
-                vi[q] = 0;
-              }
-              // fixed CTA order => deterministic; two contributors' loads in flight together (the gather is a chain of
-              // L2 round trips).  Only the first contributor can have started in an earlier tile (its tail slot).
-              auto slot_of = [&](int bb) {
-                const int wh = (bb == b_first && first_is_tail) ? 1 : 0;
-                return reinterpret_cast<const uint32_t*>(p.ws_partial) + ((size_t)bb * 2 + wh) * (N_MMA * ROWS) +
-                       (size_t)j0 * ROWS + r;
-              };
-              int bb = b_first;
+          for (int q = 0; q < 16; ++q) {
+            vf[q] = __uint_as_float(own[q]);
+            vi[q] = (int32_t)own[q];
+          }
 #pragma unroll 1
-              for (; bb + 1 <= b_last; bb += 2) {
-                const uint32_t* s0 = slot_of(bb);
-                const uint32_t* s1 = slot_of(bb + 1);
-                uint32_t t0[16], t1[16];
+          for (int c0 = 0; c0 < n_oth; c0 += 2) {
+            // two contributors x 16 columns of loads in flight (the gather is a chain of L2 round trips)
+            uint32_t t0[16], t1[16];
+            const uint32_t* s0 = slot0 + (size_t)c0 * (N_MMA * ROWS) + (size_t)j0 * ROWS;
+            const uint32_t* s1 = s0 + (size_t)(N_MMA * ROWS);
+            const bool has1 = c0 + 1 < n_oth;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) t0[q] = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0u;
+            for (int q = 0; q < 16; ++q) t0[q] = (n < p.N && m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0u;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) t1[q] = (m0 + j0 + q < p.M) ? __ldcg(s1 + q * ROWS) : 0u;
+            for (int q = 0; q < 16; ++q) t1[q] = (has1 && n < p.N && m0 + j0 + q < p.M) ? __ldcg(s1 + q * ROWS) : 0u;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  vi[q] += (int32_t)t0[q] + (int32_t)t1[q];
-                  vf[q] = (vf[q] + __uint_as_float(t0[q])) + __uint_as_float(t1[q]);
-                }
-              }
-              if (bb <= b_last) {
-                const uint32_t* s0 = slot_of(bb);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  const uint32_t v = (m0 + j0 + q < p.M) ? __ldcg(s0 + q * ROWS) : 0u;
-                  vi[q] += (int32_t)v;
-                  vf[q] += __uint_as_float(v);
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 16; ++q)
-                if (m0 + j0 + q < p.M) emit(m0 + j0 + q, (uint32_t)vi[q], vf[q]);
+            for (int q = 0; q < 16; ++q) {
+              vi[q] += (int32_t)t0[q] + (int32_t)t1[q];
+              vf[q] = (vf[q] + __uint_as_float(t0[q])) + __uint_as_float(t1[q]);
             }
+          }
+          if (n < p.N) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (m0 + j0 + q < p.M) emit(m0 + j0 + q, (uint32_t)vi[q], vf[q]);
           }
         }
       }
-      i += cnt;
-      ++seg;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty[buf]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (warp == EPI_WARP0 && walk.seg_kind(walk.nseg - 1) == streamk::SEG_OWNER) {
+    // the owner has consumed its contributors' partials: re-arm their flags for the next launch
+    const int b_last = cta_of_unit((long long)walk.seg_tile(walk.nseg - 1) * p.KT + p.KT - 1, U, G);
+    for (int c = b + 1 + lane; c <= b_last; c += 32) p.ws_flag[c] = 0u;
+  }
   if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -409,8 +407,9 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.i32_out = i32_out;
-  p.ws_sem = reinterpret_cast<unsigned int*>(ws);
-  p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 64 * 1024);
+  p.ws_flag = reinterpret_cast<unsigned int*>(ws);
+  p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_PARTIAL_OFF);
+  p.prefetch = ts_prefetch();
   p.M = M; p.N = N; p.K = K;
   p.n_tiles = ceil_div(N, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);
@@ -426,10 +425,10 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   // flight per SM (stages x 16-20 KB against the DRAM round trip), which a second resident CTA doubles
   const int per_sm = (N_MMA <= 64) ? (ts_ctas_per_sm() ? ts_ctas_per_sm() : 2) : 1;
   int grid = sm_count() * per_sm;
-  const int min_units = ts_min_units() ? ts_min_units() : (M <= 8 ? 4 : 8);
+  const int min_units = ts_min_units() ? ts_min_units() : 4;
   if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
-  const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
-  if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 64 * 1024)
+  const size_t need = streamk::WS_PARTIAL_OFF + (size_t)grid * N_MMA * ROWS * 4;
+  if (!ws || ws_bytes < need || (size_t)grid * 4 > streamk::WS_FLAGS_BYTES)
     return fail(AO_ERR_WORKSPACE, "lowp linear: workspace too small (%zu < %zu)", ws_bytes, need);
   auto kern = lowp_linear_kernel<KIND, N_MMA>;
   AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));

@@ -39,6 +39,11 @@ struct Nvfp4Fmt {
                  "l"(src), "r"(1024), "r"(smem_u32(bar))
                  : "memory");
   }
+  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p,
+                                                    int n_tile, int kc) {
+    tma_prefetch_l2_2d(tm_w, kc * 64, n_tile * ROWS);
+    bulk_prefetch_l2(p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512, 1024);
+  }
   // k-half h of row r: bytes 32h..32h+31 (k 64h..64h+63) and the four block scales of blocked tile h
   __device__ static __forceinline__ void dequant_half(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
                                                       int h, uint32_t (&out)[32]) {
@@ -97,30 +102,15 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   p.row_scale = x_scale;
   p.out_scale = b_pts;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  p.ws_sem = reinterpret_cast<unsigned int*>(ws);
-  p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 64 * 1024);
   p.aux_base = w_sf;
   p.aux_col_blocks = ceil_div(K / 16, 4);
   p.M = M; p.N = N; p.N_out = N; p.K = K; p.group_size = 16;
   p.n_tiles = ceil_div(N, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);
   p.KT = K / 128;
-  p.flags = ts_flags();
-  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 48 * 1024) : nullptr;
-  const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
-  // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  // two CTAs per SM (twice the warps hiding the per-chunk latencies) when a CTA would otherwise get fewer than
-  // 16 chunks; with longer ranges one CTA per SM leaves room for the next linear's CTA to become resident and
-  // prefetch its weights under this one (PDL), which is worth more
-  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : (units < 16LL * sm_count() ? 2 : 1);
-  int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
-  // small problems: at least 4 (decode, one token column to reduce) or 8 chunks per CTA: splitting a tile over
-  // more CTAs shortens the streaming phase but lengthens the split-tile reduction, a chain of L2 round trips
-  const int min_units = ts_min_units() ? ts_min_units() : (M <= 8 ? 4 : 8);
-  if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
-  const size_t need = 64 * 1024 + (size_t)grid * 2 * N_MMA * ROWS * 4;
-  if (!ws || ws_bytes < need || (size_t)p.n_tiles * p.m_blocks * 4 > 48 * 1024)
-    return fail(AO_ERR_WORKSPACE, "nvfp4 weight linear: workspace too small (%zu < %zu)", ws_bytes, need);
+  int grid = 0;
+  if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "nvfp4 weight linear", &grid)) return rc;
+  p.timeline = nullptr;
   auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, N_MMA>;
   AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));

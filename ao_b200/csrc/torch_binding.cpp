@@ -110,10 +110,15 @@ std::tuple<Tensor, Tensor, Tensor> int4_hqq_quantize_meta(const Tensor& w, int64
 Tensor int4_tilepacked_linear(const Tensor& x, const Tensor& qdata, int64_t group_size,
                               const Tensor& scale_and_zero, const c10::optional<Tensor>& bias,
                               int64_t n_out, int64_t impl) {
-  check_cuda(x, "x");
+  TORCH_CHECK(x.is_cuda(), "ao_b200: x must be a CUDA tensor");
   check_cuda(qdata, "qdata");
   check_cuda(scale_and_zero, "scale_and_zero");
   TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 2, "ao_b200: x must be bf16 [M, K]");
+  // rows may be strided (a column slice of a wider buffer): the TMA descriptor carries the pitch
+  TORCH_CHECK(x.size(1) <= 1 || x.stride(1) == 1, "ao_b200: x must have unit inner stride");
+  TORCH_CHECK(x.size(0) <= 1 || (x.stride(0) >= x.size(1) && x.stride(0) % 8 == 0),
+              "ao_b200: the row pitch of x must be >= K and a multiple of 8 elements");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0, "ao_b200: x must be 16-byte aligned");
   TORCH_CHECK(qdata.scalar_type() == at::kInt && qdata.dim() == 4 && qdata.size(2) == 32 && qdata.size(3) == 4, "ao_b200: qdata must be int32 [N/8, K/128, 32, 4] (inner_k_tiles=8)");
   TORCH_CHECK(scale_and_zero.scalar_type() == at::kBFloat16 && scale_and_zero.dim() == 3 && scale_and_zero.size(2) == 2, "ao_b200: scale_and_zero must be bf16 [K/g, N, 2]");
   c10::cuda::CUDAGuard guard(x.device());
@@ -133,7 +138,8 @@ Tensor int4_tilepacked_linear(const Tensor& x, const Tensor& qdata, int64_t grou
   Tensor y = at::empty({M, n_out}, x.options());
   if (M == 0) return y;
   Tensor ws = workspace_for(x);
-  AO_CALL(ao_int4_tilepacked_linear(bf16_ptr(x), (int)M, (int)K, qdata.data_ptr<int32_t>(), bf16_ptr(scale_and_zero), (int)group_size, (int)N, bias_p, bf16_ptr_mut(y), (int)n_out, ws.data_ptr(), (size_t)ws.numel(), (int)impl, cur_stream()));
+  const int64_t ldx = M > 1 ? x.stride(0) : K;
+  AO_CALL(ao_int4_tilepacked_linear_strided(bf16_ptr(x), (int)ldx, (int)M, (int)K, qdata.data_ptr<int32_t>(), bf16_ptr(scale_and_zero), (int)group_size, (int)N, bias_p, bf16_ptr_mut(y), (int)n_out, ws.data_ptr(), (size_t)ws.numel(), (int)impl, cur_stream()));
   return y;
 }
 

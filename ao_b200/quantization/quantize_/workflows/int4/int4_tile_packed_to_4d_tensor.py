@@ -113,7 +113,10 @@ def _(func, types, args, kwargs):
     k_padded = weight_tensor.qdata.shape[1] * 128
     if act.shape[-1] != k_padded:
         act = torch.nn.functional.pad(act, (0, k_padded - act.shape[-1]))
-    act = act.contiguous()
+    # a column slice of a wider buffer (e.g. the q part of a fused q|k|v output) goes to the kernel as is: its TMA
+    # descriptor carries the row pitch; anything else is made contiguous like the reference does (:278-282)
+    if not (act.stride(-1) == 1 and act.stride(0) >= act.shape[-1] and act.stride(0) % 8 == 0 and act.data_ptr() % 16 == 0):
+        act = act.contiguous()
     n_out = weight_tensor.shape[-2]
     if act.numel() == 0:
         y = act.new_empty(act.shape[0], n_out)

@@ -17,8 +17,8 @@
  *     retrievable from ao_b200_last_error() (thread-local);
  *   - kernels never synchronise the device and are CUDA-graph capturable
  *     (tensor maps are built on the host and passed by value);
- *   - `workspace` is caller-owned scratch for split-K partials + semaphores; it
- *     must be zero-initialised once (kernels restore the semaphores to zero) and
+ *   - `workspace` is caller-owned scratch for split-K partials + flags; it
+ *     must be zero-initialised once (kernels restore the flags to zero) and
  *     must not be shared by linears running concurrently on different streams.
  */
 #ifndef AO_B200_H_
@@ -84,6 +84,15 @@ int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qd
                               const uint16_t* bias, uint16_t* y, int N_out,
                               void* workspace, size_t workspace_bytes, int impl,
                               void* stream);
+/* Same with a row-strided input: row m of x starts at x + m*ldx (elements; ldx >= K, ldx % 8 == 0, x 16-byte
+ * aligned), e.g. a column slice of a wider activation buffer (the output slice of a fused q|k|v projection feeding
+ * the next linear without a copy).  The reference's handler makes such inputs contiguous first
+ * (int4_tile_packed_to_4d_tensor.py:278-282); here the TMA descriptor carries the pitch.                      */
+int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
+                                      const uint16_t* scale_and_zero, int group_size, int N,
+                                      const uint16_t* bias, uint16_t* y, int N_out,
+                                      void* workspace, size_t workspace_bytes, int impl,
+                                      void* stream);
 
 /* int8 dynamic activation x int8 weight --------------------------------------- */
 /* Per-token symmetric int8 quantisation of activations: replaces

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 torch.ops.load_library(os.path.join(ROOT, "ao_b200", "lib", "ao_b200_torch.so"))
 ops = torch.ops.ao_b200
 g = 32
-SLOT = (100 * 8 + 32) * 8
+SLOT = (100 * 8) * 8
 
 
 def mk(N, K):
