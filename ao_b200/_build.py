@@ -111,5 +111,11 @@ def build_all(force: bool = False, verbose: bool = False):
 if __name__ == "__main__":
     force = "--force" in sys.argv
     verbose = "-v" in sys.argv
+    if "--dry-run" in sys.argv:   # what would be compiled, without compiling (also: the clean-checkout test)
+        print("nvcc:", nvcc_path(), " ".join(NVCC_FLAGS))
+        for src in sorted(CSRC.glob("*.cu")):
+            print("  ", src.relative_to(ROOT.parent))
+        print("  ", (CSRC / "torch_binding.cpp").relative_to(ROOT.parent))
+        sys.exit(0)
     for p in build_all(force=force, verbose=verbose):
         print("built", p)

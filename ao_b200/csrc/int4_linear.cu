@@ -184,10 +184,10 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   p.KT = KT;
   int grid = 0;
   if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
-  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 8 stamps
+  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 16 stamps at workspace + 20 MiB
   static unsigned tl_launch = 0;
-  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_TIMELINE_OFF +
-                                                                         (size_t)(tl_launch++ & 1) * (100 * 8) * 8)
+  p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + ((size_t)20 << 20) +
+                                                                         (size_t)(tl_launch++ & 1) * (100 * 16) * 8)
                                   : nullptr;
   auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true, DBUF>
                                            : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false, DBUF>;

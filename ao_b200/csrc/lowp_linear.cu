@@ -413,7 +413,7 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   p.M = M; p.N = N; p.K = K;
   p.n_tiles = ceil_div(N, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);
-  p.KT = k_bytes / KB;
+  p.KT = ceil_div(k_bytes, KB);   // a K tail is zero-filled by TMA (out-of-bounds box elements) on both operands
   const int sf_per_row = KIND == KIND_MXF8 ? K / 32 : (KIND == KIND_NVF4 ? K / 16 : 0);
   p.sf_col_blocks_w = ceil_div(sf_per_row, 4);
   p.sf_col_blocks_x = ceil_div(sf_per_row, 4);
@@ -462,7 +462,7 @@ extern "C" int ao_int8_dyn_linear(const int8_t* xq, const float* x_scale, int M,
                                   const uint16_t* bias, uint16_t* y, void* workspace,
                                   size_t workspace_bytes, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "int8 linear: bad sizes M=%d K=%d N=%d", M, K, N);
-  AO_REQUIRE(K % 128 == 0, "int8 linear: K=%d must be a multiple of 128", K);
+  AO_REQUIRE(K % 16 == 0, "int8 linear: K=%d must be a multiple of 16 (TMA row pitch)", K);
   AO_REQUIRE(N % 8 == 0, "int8 linear: N=%d must be a multiple of 8 (reference: int8/kernels.py:48-58)", N);
   if (M == 0) return AO_OK;
   AO_REQUIRE(xq && x_scale && wq && w_scale && y, "int8 linear: null pointer");
@@ -473,7 +473,7 @@ extern "C" int ao_int8_dyn_linear(const int8_t* xq, const float* x_scale, int M,
 
 extern "C" int ao_int8_mm_i32(const int8_t* xq, int M, int K, const int8_t* wq, int N, int32_t* acc,
                               void* workspace, size_t workspace_bytes, void* stream) {
-  AO_REQUIRE(M >= 0 && K > 0 && N > 0 && K % 128 == 0, "int8 mm: bad sizes M=%d K=%d N=%d", M, K, N);
+  AO_REQUIRE(M >= 0 && K > 0 && N > 0 && K % 16 == 0, "int8 mm: bad sizes M=%d K=%d N=%d (K%%16==0)", M, K, N);
   if (M == 0) return AO_OK;
   AO_REQUIRE(xq && wq && acc, "int8 mm: null pointer");
   return lowp::dispatch<lowp::KIND_I8>(reinterpret_cast<const uint8_t*>(xq), nullptr, nullptr, M, K,
@@ -486,7 +486,7 @@ extern "C" int ao_fp8_rowwise_linear(const uint8_t* xq, const float* x_scale, in
                                      const uint16_t* bias, uint16_t* y, void* workspace,
                                      size_t workspace_bytes, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "fp8 linear: bad sizes M=%d K=%d N=%d", M, K, N);
-  AO_REQUIRE(K % 128 == 0, "fp8 linear: K=%d must be a multiple of 128", K);
+  AO_REQUIRE(K % 16 == 0, "fp8 linear: K=%d must be a multiple of 16 (reference: quantization/utils.py:663-687)", K);
   AO_REQUIRE(N % 16 == 0, "fp8 linear: N=%d must be a multiple of 16 (reference: quantization/utils.py:663-687)", N);
   if (M == 0) return AO_OK;
   AO_REQUIRE(xq && x_scale && wq && w_scale && y, "fp8 linear: null pointer");
@@ -499,7 +499,7 @@ extern "C" int ao_mxfp8_linear(const uint8_t* xq, const uint8_t* x_scale_blocked
                                const uint16_t* bias, uint16_t* y, void* workspace,
                                size_t workspace_bytes, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "mxfp8 linear: bad sizes M=%d K=%d N=%d", M, K, N);
-  AO_REQUIRE(K % 128 == 0, "mxfp8 linear: K=%d must be a multiple of 128", K);
+  AO_REQUIRE(K % 32 == 0, "mxfp8 linear: K=%d must be a multiple of 32 (mx_tensor.py:244-246)", K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(xq && x_scale_blocked && wq && w_scale_blocked && y, "mxfp8 linear: null pointer");
   return lowp::dispatch<lowp::KIND_MXF8>(xq, x_scale_blocked, nullptr, M, K, wq, w_scale_blocked, nullptr, N,

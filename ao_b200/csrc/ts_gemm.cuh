@@ -9,10 +9,14 @@
 //     the CTAs; split tiles are finished by their OWNER CTA from the contributors' published partials
 //   * 16 warps in four warpgroups, 64 registers per thread, 256 TMEM columns, ~105 KB smem (two CTAs fit per SM,
 //     so the next linear's CTA is resident -- PDL -- and has its weights in flight while this one finishes):
-//       WG0, WG1 (warps 0-7): dequant, alternating chunks: ld.shared -> unpack/scale in bf16x2, one 64-k half row
-//                  (32 registers) at a time -> tcgen05.st of the bf16 A operand into one of the TMEM A stages
-//       WG2 (warps 8-11): epilogue: tcgen05.ld of a finished accumulator (double-buffered in TMEM: overlaps the
-//                  next segment's MMAs), bias / scales, store or publish
+//       WG0..WG2 (warps 0-11): dequant, chunk i belongs to warpgroup i % 3: ld.shared -> unpack/scale in bf16x2,
+//                  one 64-k half row (32 registers) at a time -> tcgen05.st of the bf16 A operand into one of the
+//                  TMEM A stages.  A chunk is a serial chain of waits (weights landed, A stage free, TMEM store
+//                  done) around ~400 instructions, so what counts is how many chunks are in flight per SM: three.
+//                  The same warpgroups run the epilogues (tcgen05.ld of a finished accumulator -- double-buffered
+//                  in TMEM, so it overlaps the next segment's MMAs -- bias / scales, store or publish): the
+//                  warpgroup that dequantised a segment's last chunk finishes the segment after its NEXT chunk,
+//                  when the accumulator is long complete, so nothing ever blocks on the tensor pipe mid-stream
 //       WG3: warp 12 weight TMA producer (never waits for the previous kernel; also runs the L2 prefetch of the
 //                  chunks ahead of the ring), warp 14 activation TMA producer (after griddepcontrol.wait),
 //                  warp 13 MMA issuer
@@ -47,7 +51,7 @@ constexpr int KCHUNK = 128;
 constexpr int W_BYTES = ROWS * KCHUNK / 2;  // 8 KiB of 4-bit weights per chunk
 constexpr int AUX_BYTES = 2048;             // scales per chunk (<= 2 KiB), 1 KiB aligned slot
 constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage (128 k / 2)
-constexpr int DEQ_WARPS = 8, EPI_WARP0 = 8, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14;
+constexpr int DEQ_WGS = 3, DEQ_WARPS = 4 * DEQ_WGS, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14;
 constexpr int WSTAGE_BYTES = W_BYTES + AUX_BYTES;  // one weight stage: packed nibbles + scales
 constexpr int NUM_THREADS = 16 * 32;
 
@@ -60,9 +64,10 @@ struct Cfg {
   static constexpr int A_COL0 = D_COLS <= 64 ? 64 : (D_COLS <= 128 ? 128 : 256);
   static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4; also the depth of the activation ring
   static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 172 * 1024;
-  // weight stages (8, 8, 6 or 4): even, so that a stage is always consumed by the same dequant warpgroup and
-  // every waiter of a barrier observes each of its phases
-  static constexpr int STAGES = ((BUDGET - A_STAGES * X_BYTES) / WSTAGE_BYTES) & ~1;
+  // weight stages (8, 8, 6 or 5).  A stage is consumed by whichever warpgroup its chunk belongs to; a consumer can
+  // never be two phases away from the barrier it waits on (chunk i - STAGES was consumed before chunk i - 3 could
+  // be stored, chunk i + STAGES cannot be issued before chunk i is consumed), so parity waits do not alias
+  static constexpr int STAGES = (BUDGET - A_STAGES * X_BYTES) / WSTAGE_BYTES;
   static constexpr int X_OFF = STAGES * WSTAGE_BYTES;
   static constexpr int BAR_OFF = X_OFF + A_STAGES * X_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)BAR_OFF + 1024 + 1024;
@@ -82,7 +87,7 @@ struct Params {
   int aux_col_blocks;
   int prefetch;  // chunks of L2 prefetch ahead of the shared-memory ring (0 = none)
   int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs
-  unsigned long long* timeline;  // debug: per-CTA [8] timestamps (AO_B200_TIMELINE=1), else null
+  unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -136,7 +141,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   uint64_t* afull = sempty + S;       // [T][2] 4 dequant warps (A stage stored) + activation TMA (arrive.expect_tx)
   uint64_t* aempty = afull + 2 * T;   // [T][2] MMA commit: A stage and activation slot both free
   uint64_t* dfull = aempty + 2 * T;   // [2]   accumulator of a segment complete
-  uint64_t* dempty = dfull + 2;       // [2]   4 epilogue warps
+  uint64_t* dempty = dfull + 2;       // [2]   the 4 warps of the warpgroup that ran the segment's epilogue
   uint64_t* dlast = dempty + 2;       // [1]   accumulator of the CTA's LAST segment complete (single phase: any warp
                                       //       may wait on it without having followed the dfull phases)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dlast + 1);
@@ -152,7 +157,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     if (TL && p.timeline && b < 100) {   // absolute globaltimer ns: comparable across back-to-back kernels
       unsigned long long gt;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-      p.timeline[(size_t)b * 8 + e] = gt;
+      p.timeline[(size_t)b * 16 + e] = gt;
     }
   };
   if (threadIdx.x == 0) stamp(0);
@@ -229,6 +234,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const float osc = p.out_scale ? *p.out_scale : 1.f;
     const float* slot0 = p.ws_partial + (size_t)(b + 1) * (N_MMA * ROWS) + r;
     streamk::wait_flags(p.ws_flag + b + 1, n_oth, lane);
+    if (helper == 0 && r == 0) stamp(8);
     if (p.M - m0 == 1) {
       // decode, one token column: every contributor's value in flight at once
       if (helper != 0) return;
@@ -274,23 +280,82 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (row_ok) emit8(v, n, m0 + j0, bias, osc);
     }
   };
-  // helpers (the three non-epilogue warpgroups) of a cooperative OWNER finish
+  // cooperative OWNER finish of the last segment: every warpgroup takes every fourth group of 8 token columns
   auto coop_help = [&](int helper) {
     pdl_wait();   // outputs and workspace belong to the previous kernel until it has completed (long past by now)
     while (!mbar_try_wait(dlast, 0)) __nanosleep(32);   // the producers get here early: do not steal issue slots
     tc_fence_after();
+    if (helper == 0 && (warp & 3) == 0 && lane == 0) stamp(6);
     const int q4 = warp & 3;
     finish_owner(last_tile, tmem_base + ((uint32_t)(q4 * 32) << 16) + C::d_col(last_buf), q4 * 32 + lane, helper, 4);
+    if (helper == 0 && (warp & 3) == 0 && lane == 0) stamp(7);
   };
 
   if (warp < DEQ_WARPS) {
-    // ------------------------------------------------------------ dequant warpgroups (0: even, 1: odd chunks)
+    // ------------------------------------------------------------ dequant warpgroups: chunk i belongs to WG i % 3
     const int wg = warp >> 2, q4 = warp & 3;
     const int r = q4 * 32 + lane;  // weight row of the tile == TMEM lane
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    // ring positions of chunk i = wg, wg + 2, ... kept incrementally (the integer pipe is the bottleneck here)
-    int s = wg, sph = 0, t = wg % T, k = wg / T;
-    for (int i = wg; i < nunits; i += 2) {
+    bool waited_prev = false;   // griddepcontrol.wait executed (outputs / workspace belong to the previous kernel)
+
+    // Epilogue of a segment that is NOT the CTA's last one (FULL or CONTRIB), by this warpgroup.
+    auto epilogue = [&](int seg) {
+      if (!waited_prev) { pdl_wait(); waited_prev = true; }
+      const int tile = walk.seg_tile(seg);
+      const int kind = walk.seg_kind(seg);
+      const int buf = seg % DBUF;
+      mbar_wait(&dfull[buf], (seg / DBUF) & 1);
+      tc_fence_after();
+      const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
+      const uint32_t d_lane = lane_taddr + C::d_col(buf);
+      if (kind == streamk::SEG_FULL) {
+        // the whole K range of this tile was ours: straight to the output
+        const float bias = (p.bias && n < p.N_out) ? __bfloat162float(p.bias[n]) : 0.f;
+        const float osc = p.out_scale ? *p.out_scale : 1.f;
+#pragma unroll 1
+        for (int j = 0; j < N_MMA; j += 8) {
+          if (m0 + j >= p.M) break;
+          float v[8];
+          tmem_ld_x8(d_lane + j, v);
+          if (n < p.N_out) emit8(v, n, m0 + j, bias, osc);
+        }
+      } else {
+        // CONTRIB: publish the partial (column-major slot: coalesced across the 128 rows), then raise this CTA's flag
+        float* slot = p.ws_partial + (size_t)b * (N_MMA * ROWS) + r;
+#pragma unroll 1
+        for (int j = 0; j < N_MMA; j += 8) {
+          if (m0 + j >= p.M) break;
+          float v[8];
+          tmem_ld_x8(d_lane + j, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS], v[q]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // all 128 rows stored (cta-scope order) ...
+        if (q4 == 0 && lane == 0) streamk::st_release_u32(p.ws_flag + b, 1u);   // ... then one gpu-scope release
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty[buf]);
+    };
+    // the segment whose last chunk is e belongs to warpgroup e % 3, which runs its epilogue after its next chunk
+    int ep_seg = 0;
+    auto seg_end = [&](int sg) { return walk.seg_begin(sg) + walk.seg_count(sg) - 1; };
+    auto run_epilogues = [&](int before_chunk) {
+      while (ep_seg < seg_last) {
+        const int e = seg_end(ep_seg);
+        if (e % DEQ_WGS == wg) {
+          if (e >= before_chunk) break;
+          epilogue(ep_seg);
+        }
+        ++ep_seg;
+      }
+    };
+
+    // ring positions of chunk i = wg, wg + 3, ... kept incrementally (the integer pipe is busy enough here)
+    int s = wg % S, sph = 0, t = wg % T, k = wg / T;
+    for (int i = wg; i < nunits; i += DEQ_WGS) {
       const uint32_t st = smem_u32(smem + (size_t)s * WSTAGE_BYTES);
       const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
       mbar_wait(&wfull[s], sph);
@@ -298,16 +363,6 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       // the row in two 64-k halves (32 registers of output each): half 0 is computed before the A stage is
       // known to be free, so the wait overlaps its arithmetic
       uint32_t out[32];
-      if (p.flags & 1) {   // bring-up: skip the dequant arithmetic and the TMEM stores (timing experiments only)
-        if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);
-        __syncwarp();
-        if (elect_one()) { mbar_arrive(&sempty[s]); mbar_arrive(&afull[t * 2 + (k & 1)]); }
-        s += 2;
-        if (s >= S) { s -= S; sph ^= 1; }
-        t += 2;
-        if (t >= T) { t -= T; ++k; }
-        continue;
-      }
       Fmt::dequant_half(p, st, st + W_BYTES, r, 0, out);
       if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);  // MMAs of chunk i - T are done
       tc_fence_after();
@@ -320,12 +375,31 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (elect_one()) mbar_arrive(&afull[t * 2 + (k & 1)]);
-      s += 2;
+      s += DEQ_WGS;
       if (s >= S) { s -= S; sph ^= 1; }
-      t += 2;
-      if (t >= T) { t -= T; ++k; }
+      t += DEQ_WGS;
+      while (t >= T) { t -= T; ++k; }
+      run_epilogues(i);   // segments this warpgroup's EARLIER chunks completed: their accumulators are long done
     }
-    if (coop) coop_help(1 + wg);
+    run_epilogues(nunits);   // whatever is left of the segments before the last one
+    // ---- the CTA's last segment
+    if (coop) {
+      coop_help(wg);
+    } else if (wg == (nunits - 1 + 1) % DEQ_WGS) {
+      // the warpgroup that did NOT dequantise the last chunk has been idle longest: it finishes the segment
+      if (!waited_prev) { pdl_wait(); waited_prev = true; }
+      while (!mbar_try_wait(dlast, 0)) __nanosleep(32);
+      tc_fence_after();
+      if (warp == (wg << 2) && lane == 0) stamp(6);
+      const uint32_t d_lane = lane_taddr + C::d_col(last_buf);
+      if (last_kind == streamk::SEG_OWNER) {
+        finish_owner(last_tile, d_lane, r, 0, 1);
+      } else {
+        // FULL or CONTRIB as the last segment: same code as mid-stream (dfull of the last segment == dlast)
+        epilogue(seg_last);
+      }
+      if (warp == (wg << 2) && lane == 0) stamp(7);
+    }
   } else if (warp >= TMA_WARP) {
     if (warp == TMA_WARP) {
       // ---------------------------------------------------------- weight producer.  Weights never depend on the
@@ -415,61 +489,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       }
     }
     if (coop) coop_help(3);
-  } else {
-    // ------------------------------------------------------------ epilogue warps (8..11)
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    pdl_wait();
-    for (int seg = 0; seg < walk.nseg; ++seg) {
-      const int tile = walk.seg_tile(seg);
-      const int kind = walk.seg_kind(seg);
-      const int buf = seg % DBUF;
-      while (!mbar_try_wait(&dfull[buf], (seg / DBUF) & 1)) __nanosleep(64);  // long wait: do not steal issue slots
-      tc_fence_after();
-      if (seg == seg_last && (warp == EPI_WARP0 && lane == 0)) stamp(6);
-      const int n_tile = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-      const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
-      const uint32_t d_lane = lane_taddr + C::d_col(buf);
-      if (kind == streamk::SEG_FULL) {
-        // the whole K range of this tile was ours: straight to the output
-        const float bias = (p.bias && n < p.N_out) ? __bfloat162float(p.bias[n]) : 0.f;
-        const float osc = p.out_scale ? *p.out_scale : 1.f;
-#pragma unroll 1
-        for (int j = 0; j < N_MMA; j += 8) {
-          if (m0 + j >= p.M) break;
-          float v[8];
-          tmem_ld_x8(d_lane + j, v);
-          if (n < p.N_out) emit8(v, n, m0 + j, bias, osc);
-        }
-      } else if (kind == streamk::SEG_CONTRIB) {
-        // publish the partial (column-major slot: coalesced across the 128 rows), then raise this CTA's flag
-        float* slot = p.ws_partial + (size_t)b * (N_MMA * ROWS) + r;
-#pragma unroll 1
-        for (int j = 0; j < N_MMA; j += 8) {
-          if (m0 + j >= p.M) break;
-          float v[8];
-          tmem_ld_x8(d_lane + j, v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (m0 + j + q < p.M) __stcg(&slot[(j + q) * ROWS], v[q]);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // all 128 rows stored (cta-scope order) ...
-        if (warp == EPI_WARP0 && lane == 0) streamk::st_release_u32(p.ws_flag + b, 1u);   // ... then one gpu-scope release
-      } else {
-        finish_owner(tile, d_lane, r, 0, coop ? 4 : 1);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dempty[buf]);
-    }
-    if (warp == EPI_WARP0 && lane == 0) stamp(7);
   }
 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (last_kind == streamk::SEG_OWNER && warp == EPI_WARP0) {
+  if (threadIdx.x == 0) stamp(9);
+  if (last_kind == streamk::SEG_OWNER && warp == 0) {
     // every warpgroup has read the contributors' partials: re-arm their flags for the next launch
     const int b_last = streamk::cta_of_unit((long long)last_tile * p.KT + p.KT - 1, U, G);
     for (int c = b + 1 + lane; c <= b_last; c += 32) p.ws_flag[c] = 0u;
@@ -483,16 +509,18 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------ host side
 // Grid choice + workspace carve-up shared by the launchers of this kernel.
-//   * at most one CTA per SM x resident CTAs (forward progress of the owner protocol, streamk.cuh)
-//   * two CTAs per SM (twice the warps hiding the per-chunk latencies) when a CTA would otherwise get fewer than
-//     16 chunks; with longer ranges one CTA per SM leaves room for the next linear's CTA to become resident under
-//     this one (PDL), which is worth more
+//   * one CTA per SM: the second slot of every SM belongs to the NEXT linear's CTA, which becomes resident under
+//     this one (PDL) and has its first weights in flight while this kernel finishes.  A grid that fills both slots
+//     makes each kernel's CTAs wait for the previous kernel's CTAs to exit, so one late CTA delays a CTA of every
+//     following kernel (measured: 2 CTAs/SM 92.7 us per Llama-3-8B layer at bs=32, 1 CTA/SM 74.3;
+//     profiles/r02_call_a.log).  Also keeps the grid within the resident capacity, which the owner protocol needs
+//     for forward progress (streamk.cuh)
 //   * never fewer than `min_units` chunks per CTA: splitting a tile over more CTAs shortens the streaming phase but
 //     lengthens the owner's gather
 template <int N_MMA>
 inline int plan(Params& p, void* ws, size_t ws_bytes, const char* what, int* grid_out) {
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
-  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : (units < 16LL * sm_count() ? 2 : 1);
+  const int per_sm = ts_ctas_per_sm() ? ts_ctas_per_sm() : 1;
   int grid = sm_count() * (N_MMA <= 64 ? per_sm : 1);
   const int min_units = ts_min_units() ? ts_min_units() : 4;
   if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;

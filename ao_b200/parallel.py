@@ -16,16 +16,33 @@ from ao_b200.utils import TorchAOBaseTensor
 
 def packed_buffers(module: torch.nn.Module) -> List[Tuple[str, torch.Tensor]]:
     """Every plain tensor that makes up the quantized parameters of ``module`` (qdata, scales, ...), in a
-    deterministic order, plus ordinary parameters/buffers."""
-    out = []
-    for name, p in list(module.named_parameters()) + list(module.named_buffers()):
-        t = p.data if isinstance(p, torch.nn.Parameter) else p
+    deterministic order, plus ordinary parameters/buffers.  Members of a fused group (``ao_b200.fusion``) hold views
+    of the group's storage: the group's own (contiguous) buffers are listed once, under the first member's name."""
+    from ao_b200.fusion import FusedLinearMember
+
+    def flat(name, t, out):
         if isinstance(t, TorchAOBaseTensor):
             names, _ = t.__tensor_flatten__()
             for n in names:
                 out.append((f"{name}.{n}", getattr(t, n)))
-        else:
+        elif t is not None:
             out.append((name, t))
+
+    out, seen_groups, member_params = [], set(), set()
+    for mod_name, mod in module.named_modules():
+        if isinstance(mod, FusedLinearMember):
+            g = mod._group
+            for pn, _ in mod.named_parameters(recurse=False):
+                member_params.add(f"{mod_name}.{pn}" if mod_name else pn)
+            if id(g) not in seen_groups:
+                seen_groups.add(id(g))
+                prefix = f"{mod_name}.fused" if mod_name else "fused"
+                flat(f"{prefix}.weight", g.weight, out)
+                flat(f"{prefix}.bias", g.bias, out)
+    for name, p in list(module.named_parameters()) + list(module.named_buffers()):
+        if name in member_params:
+            continue
+        flat(name, p.data if isinstance(p, torch.nn.Parameter) else p, out)
     return out
 
 

@@ -8,6 +8,8 @@ from dataclasses import dataclass
 from enum import Enum
 from typing import Optional
 
+import logging
+
 import torch
 
 from ao_b200._native import require_sm100
@@ -24,6 +26,9 @@ from .nvfp4_tensor import (NVFP4Tensor, QuantizeTensorToFloat8ActKwargs, Quantiz
 class QuantizationStep(str, Enum):
     PREPARE = "prepare"
     CONVERT = "convert"
+
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass
@@ -56,6 +61,19 @@ def _check_nvfp4_shape(weight):
         raise RuntimeError(f"NVFP4 only supports weight shape with last 2 dims divisible by 16, got {weight.shape}")
 
 
+def _nvfp4_kernel_compat(weight, k_multiple: int) -> bool:
+    """The sm_100a kernels stream K in chunks whose block-scale tiles must exist in full: K % 256 for nvfp4 x nvfp4
+    (lowp_linear.cu), K % 128 for the weight-only / fp8-activation kernel (ts_gemm.cuh).  The reference accepts any
+    K % 16 (inference_workflow.py:248-251); such a layer is left unquantized here, with a log line, the way the int4
+    and float8 flows skip incompatible shapes (quant_api.py:549-553, quantization/utils.py:663-687) -- never
+    quantized into something whose first forward raises."""
+    if weight.shape[-1] % k_multiple != 0:
+        logger.info(f"Skipping NVFP4 quantization: in_features={weight.shape[-1]} is not a multiple of {k_multiple} "
+                    f"(kernel K-chunk); weight shape {tuple(weight.shape)} stays {weight.dtype}")
+        return False
+    return True
+
+
 @dataclass
 class NVFP4DynamicActivationNVFP4WeightConfig(AOBaseConfig):
     use_triton_kernel: bool = True   # accepted for compatibility; the CUDA quantizer is always used
@@ -76,6 +94,8 @@ def _nvfp4_inference_linear_transform(module, config, *, parameter_name="weight"
     if torch.cuda.is_available():
         require_sm100()
     assert weight.dim() == 2, "3D (MoE) weights are out of scope"
+    if not _nvfp4_kernel_compat(weight, 256):
+        return module
     pts = per_tensor_amax_to_scale(torch.max(torch.abs(weight))) if config.use_dynamic_per_tensor_scale else None
     act = QuantizeTensorToNVFP4Kwargs(use_dynamic_per_tensor_scale=config.use_dynamic_per_tensor_scale,
                                       use_triton_kernel=config.use_triton_kernel, is_swizzled_scales=True)
@@ -95,6 +115,8 @@ def _nvfp4_weight_only_linear_transform(module, config, *, parameter_name="weigh
     weight = getattr(module, parameter_name)
     assert weight.dim() == 2, "3D weights not yet supported in this workflow"
     _check_nvfp4_shape(weight)
+    if not _nvfp4_kernel_compat(weight, 128):
+        return module
     pts = per_tensor_amax_to_scale(torch.max(torch.abs(weight))) if config.use_dynamic_per_tensor_scale else None
     qw = NVFP4Tensor.to_nvfp4(weight.contiguous(), per_tensor_scale=pts, is_swizzled_scales=True, act_quant_kwargs=None)
     return _set_quantized_param(module, parameter_name, qw)
@@ -114,6 +136,8 @@ def _nvfp4_weight_fp8_act_transform(module, config, *, parameter_name="weight"):
     weight = getattr(module, parameter_name)
     assert weight.dim() == 2
     _check_nvfp4_shape(weight)
+    if not _nvfp4_kernel_compat(weight, 128):
+        return module
     pts = per_tensor_amax_to_scale(torch.max(torch.abs(weight))) if config.use_dynamic_per_tensor_scale else None
     qw = NVFP4Tensor.to_nvfp4(weight.contiguous(), per_tensor_scale=pts, is_swizzled_scales=True,
                               act_quant_kwargs=QuantizeTensorToFloat8ActKwargs())

@@ -192,6 +192,13 @@ class Int8DynamicActivationInt8WeightConfig(AOBaseConfig):
 
 def _int8_dynamic_activation_int8_weight_quantize_tensor(weight, config):
     a, w = Int8Tensor._normalize_granularity(config.granularity)
+    if weight.shape[-1] % 16 != 0 or weight.shape[-2] % 8 != 0:
+        # the reference's cuBLAS path needs K % 8 == 0 and N % 8 == 0 and otherwise falls back to a CPU matmul
+        # (int8/kernels.py:48-58); this engine has no fallback and its TMA row pitch needs K % 16 == 0: leave the
+        # layer unquantized, with a log line, like the int4 / float8 flows do for incompatible shapes
+        logger.info(f"Skipping int8 dynamic quantization: weight shape {tuple(weight.shape)} needs in_features % 16 == 0 "
+                    f"and out_features % 8 == 0 for the sm_100a kernel")
+        return weight
     return Int8Tensor.from_hp(
         weight, granularity=w, mapping_type=MappingType.SYMMETRIC,
         act_quant_kwargs=QuantizeTensorToInt8Kwargs(granularity=a, mapping_type=config.act_mapping_type,

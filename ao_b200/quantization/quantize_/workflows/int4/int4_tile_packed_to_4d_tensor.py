@@ -115,7 +115,8 @@ def _(func, types, args, kwargs):
         act = torch.nn.functional.pad(act, (0, k_padded - act.shape[-1]))
     # a column slice of a wider buffer (e.g. the q part of a fused q|k|v output) goes to the kernel as is: its TMA
     # descriptor carries the row pitch; anything else is made contiguous like the reference does (:278-282)
-    if not (act.stride(-1) == 1 and act.stride(0) >= act.shape[-1] and act.stride(0) % 8 == 0 and act.data_ptr() % 16 == 0):
+    # (alignment from the storage offset, not data_ptr(): the handler must stay traceable with fake tensors)
+    if not (act.stride(-1) == 1 and act.stride(0) >= act.shape[-1] and act.stride(0) % 8 == 0 and act.storage_offset() % 8 == 0):
         act = act.contiguous()
     n_out = weight_tensor.shape[-2]
     if act.numel() == 0:

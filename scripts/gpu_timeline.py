@@ -13,7 +13,8 @@ sys.path.insert(0, ROOT)
 torch.ops.load_library(os.path.join(ROOT, "ao_b200", "lib", "ao_b200_torch.so"))
 ops = torch.ops.ao_b200
 g = 32
-SLOT = (100 * 8) * 8
+SLOT = (100 * 16) * 8
+BASE = 20 << 20
 
 
 def mk(N, K):
@@ -23,12 +24,12 @@ def mk(N, K):
 
 
 def slot(ws, i):
-    return ws[48 * 1024 + i * SLOT: 48 * 1024 + i * SLOT + 100 * 64].view(torch.int64).reshape(100, 8).cpu()
+    return ws[BASE + i * SLOT: BASE + (i + 1) * SLOT].view(torch.int64).reshape(100, 16).cpu()
 
 
 Ms = (1, 32) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split(','))
 shapes = [(14336, 4096)] if len(sys.argv) < 3 else [tuple(int(v) for v in sys.argv[2].split('x'))]
-names = ["entry", "prologue", "pdl_wait", "w_landed", "mma_first", "mma_last", "acc_ready", "done"]
+names = ["entry", "prologue", "pdl_wait", "w_landed", "mma_first", "mma_last", "acc_ready", "done", "flags_ok", "exit"]
 for M in Ms:
     for (N, K) in shapes:
         x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -37,20 +38,22 @@ for M in Ms:
             ops.int4_tilepacked_linear(x, ws_list[0][0], g, ws_list[0][1], None, N, 1)
         torch.cuda.synchronize()
         ws = ops.debug_workspace(x)
-        ws[48 * 1024: 64 * 1024].zero_()
+        ws[BASE: BASE + 2 * SLOT].zero_()
         torch.cuda.synchronize()
         for c in range(4):   # chain of 4; slots hold launches 2 and 3 (or 3 and 2)
             ops.int4_tilepacked_linear(x, ws_list[c][0], g, ws_list[c][1], None, N, 1)
         torch.cuda.synchronize()
         a, b = slot(ws, 0), slot(ws, 1)
-        ua, ub = a[a[:, 7] > 0], b[b[:, 7] > 0]
+        ua, ub = a[a[:, 9] > 0], b[b[:, 9] > 0]
         first, second = (ua, ub) if ua[:, 0].min() < ub[:, 0].min() else (ub, ua)
         t0 = int(first[:, 0].min())
         print(f"M={M} N={N} K={K}: chain of 4, last two kernels (us since the earlier one's first CTA entry; min / median / max over CTAs)")
         for nm, kern in (("k", first), ("k+1", second)):
             parts = []
-            for e in range(8):
-                col = (kern[:, e] - t0).float() / 1e3
+            for e in range(10):
+                col = (kern[:, e][kern[:, e] > 0] - t0).float() / 1e3
+                if col.numel() == 0:
+                    continue
                 parts.append(f"{names[e]} {col.min():.1f}/{col.median():.1f}/{col.max():.1f}")
             print(f"   {nm:4s}" + "  ".join(parts))
-        print(f"   launch-to-launch: {(int(second[:, 7].max()) - int(first[:, 7].max())) / 1e3:.2f} us  (end of k+1 minus end of k)")
+        print(f"   launch-to-launch: {(int(second[:, 9].max()) - int(first[:, 9].max())) / 1e3:.2f} us  (end of k+1 minus end of k)")

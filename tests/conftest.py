@@ -35,10 +35,11 @@ def _ensure_native_built():
     prebuilt files travel with the snapshot; mtimes are not reliable there, so no staleness check)."""
     import os
 
-    from ao_b200 import _build
-    from ao_b200._native import native_lib_paths
+    import __graft_entry__ as entry
 
-    if not all(p.exists() for p in native_lib_paths()) or os.environ.get("AO_B200_FORCE_BUILD"):
+    _build = entry.load_build_module()   # by path: the package itself cannot be imported before the libraries exist
+    libs = (_build.LIB / "libao_b200.so", _build.LIB / "ao_b200_torch.so")
+    if not all(p.exists() for p in libs) or os.environ.get("AO_B200_FORCE_BUILD"):
         _build.build_all(force=True)
     from oracle import oracle as o
 

@@ -327,3 +327,25 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|ao_oracle|libao_oracle", txt, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_clean_checkout_can_build_itself(tmp_path):
+    """A fresh checkout has no ao_b200/lib (git-ignored): every build entry point must work without importing the
+    package's native side first, and a plain `import ao_b200` must still fail loudly."""
+    import shutil
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "repo"
+    shutil.copytree(root, dst, ignore=shutil.ignore_patterns("lib", "_build", "_ref", ".git", "gpurun_out", "__pycache__",
+                                                             "profiles", "golden", "*.so", "*.o", ".pytest_cache"))
+    env = dict(os.environ, PYTHONPATH=str(dst))
+    env.pop("AO_B200_BUILDING", None)
+    run = lambda *a: subprocess.run([sys.executable, *a], cwd=dst, env=env, capture_output=True, text=True, timeout=120)
+    r = run("-m", "ao_b200._build", "--dry-run")
+    assert r.returncode == 0 and "int4_linear.cu" in r.stdout, r.stderr[-2000:]
+    r = run("-c", "import __graft_entry__ as e; m = e.load_build_module(); print(sorted(p.name for p in m.CSRC.glob('*.cu')))")
+    assert r.returncode == 0 and "lowp_linear.cu" in r.stdout, r.stderr[-2000:]
+    r = run("-c", "import ao_b200")
+    assert r.returncode != 0 and "native library not built" in r.stderr
