@@ -86,7 +86,7 @@ struct Params {
   int n_tiles, m_blocks, KT;   // KT = K/128
   int aux_col_blocks;
   int prefetch;  // chunks of L2 prefetch ahead of the shared-memory ring (0 = none)
-  int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs
+  int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 2 = skip MMAs, 4 = no activation loads after the first ring-full
   unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
 };
 
@@ -443,9 +443,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         if (elect_one()) {
           uint8_t* xs = smem + C::X_OFF + (size_t)t * C::X_BYTES;
           const int m0 = (tile / p.n_tiles) * N_MMA, k0 = kc * KCHUNK;
-          mbar_expect_tx(full, C::X_BYTES);
-          tma_load_2d(xs, &tm_x, full, k0, m0, pol_x);
-          tma_load_2d(xs + N_MMA * 128, &tm_x, full, k0 + 64, m0, pol_x);
+          if ((p.flags & 4) && i >= T) {
+            mbar_arrive(full);   // bring-up: no activation loads after the first ring-full (garbage results)
+          } else {
+            mbar_expect_tx(full, C::X_BYTES);
+            tma_load_2d(xs, &tm_x, full, k0, m0, pol_x);
+            tma_load_2d(xs + N_MMA * 128, &tm_x, full, k0 + 64, m0, pol_x);
+          }
         }
         __syncwarp();
         if (++t == T) { t = 0; ++k; }

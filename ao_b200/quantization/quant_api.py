@@ -85,7 +85,7 @@ def quantize_(model: torch.nn.Module, config: AOBaseConfig,
               device: Optional[torch.types.Device] = None):
     """Convert the weight of linear modules in ``model`` according to ``config``, in place; returns None."""
     if isinstance(config, FqnToConfig):
-        if filter_fn is not None and filter_fn is not _is_linear:
+        if filter_fn is not None:   # the default `_is_linear` included, exactly like the reference (quant_api.py:286-290)
             raise ValueError("Custom filter_fn and FqnToConfig were both specified. Only filter_fn=None is supported "
                              "when FqnToConfig is specified.")
         named_modules = dict(model.named_modules())
@@ -326,26 +326,27 @@ def _apply(module, c, parameter_name=None):
 
 
 def _fqn_to_config_handler(module: torch.nn.Module, fqn: str, config: FqnToConfig):
-    """Precedence: exact parameter fqn > exact module fqn > parameter regex > module regex > _default."""
+    """Same order as the reference (quant_api.py:1638-1701): exact parameter fqns first (several may match; a `None`
+    config takes the parameter out of the regex pass), then -- only when no parameter matched -- the exact module
+    fqn; then EVERY regex that fully matches a remaining top-level parameter, in dict order; then -- only when still
+    nothing matched -- the first module-fqn regex, and finally `_default`."""
     found = False
-    params = list(_top_level_params(module, fqn))
     remaining = []
-    for name, _, pfqn in params:
+    for name, _, pfqn in _top_level_params(module, fqn):
         if pfqn in config.fqn_to_config:
             found = True
-            module = _apply(module, config.fqn_to_config[pfqn], parameter_name=name)
+            c = config.fqn_to_config[pfqn]
+            if c is not None:
+                module = _apply(module, c, parameter_name=name)
         else:
             remaining.append((name, pfqn))
-    if found:
-        return module
-    if fqn in config.fqn_to_config:
+    if not found and fqn in config.fqn_to_config:
         return _apply(module, config.fqn_to_config[fqn])
     for name, pfqn in remaining:
         for pat, c in config.fqn_to_config.items():
             if pat.startswith("re:") and re.fullmatch(pat[3:], pfqn):
                 found = True
                 module = _apply(module, c, parameter_name=name)
-                break
     if found:
         return module
     for pat, c in config.fqn_to_config.items():

@@ -24,6 +24,8 @@ CASES = {
     "exact_beats_regex": [("re:.*", "R"), ("mlp.up", "E")],
     "param_none_then_regex": [("attn.q_proj.weight", None), ("re:.*\\\\.weight", "W")],
     "bias_param": [("attn.q_proj.bias", "B")],
+    "exact_param_then_regex_on_the_other_params": [("attn.q_proj.weight", "A"), ("re:.*bias", "B")],
+    "two_regexes_on_different_params": [("re:.*q_proj\\.weight", "W"), ("re:.*q_proj\\.bias", "B")],
 }
 
 
