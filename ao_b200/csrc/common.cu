@@ -124,12 +124,12 @@ int ts_min_units() {
   return v;
 }
 
-int ts_prefetch() {
+int ts_producers() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AO_B200_TS_PREFETCH");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 4096) v = 0;
+    const char* e = getenv("AO_B200_TS_PRODUCERS");
+    v = e ? atoi(e) : 2;
+    if (v != 1) v = 2;
   }
   return v;
 }

@@ -48,12 +48,6 @@ struct Int4Fmt {
     tma_load_3d(w_dst, tm_w, bar, 0, 4 * kc, n_tile * (ROWS / 8), policy);
     tma_load_2d(aux_dst, tm_sz, bar, n_tile * ROWS, (kc * KCHUNK) / p.group_size, policy);
   }
-  // HBM -> L2 of the same two boxes (no shared memory): issued `prefetch` chunks ahead of the ring
-  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap* tm_sz,
-                                                    const tsg::Params& p, int n_tile, int kc) {
-    tma_prefetch_l2_3d(tm_w, 0, 4 * kc, n_tile * (ROWS / 8));
-    tma_prefetch_l2_2d(tm_sz, n_tile * ROWS, (kc * KCHUNK) / p.group_size);
-  }
   // thread r (= TMEM lane = weight row of the tile), k-half h: 32 packed bytes + up to 2 (s,z) pairs -> 32 bf16x2
   // (out[c] = k pair 64h + 2c, 64h + 2c + 1).  The row's 64 bytes are four 16-byte lane words (tinygemm word
   // wd = k 32wd..32wd+31 sits at byte 4wd of each); half h needs words 2h, 2h+1 = the 8 bytes at +8h of each.
@@ -184,10 +178,10 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   p.KT = KT;
   int grid = 0;
   if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
-  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 16 stamps at workspace + 20 MiB
+  // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 16 stamps + 8 chunks x 8 fine stamps at workspace + 20 MiB
   static unsigned tl_launch = 0;
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + ((size_t)20 << 20) +
-                                                                         (size_t)(tl_launch++ & 1) * (100 * 16) * 8)
+                                                                         (size_t)(tl_launch++ & 1) * (100 * 16 + 64) * 8)
                                   : nullptr;
   auto kern = (p.timeline && N_MMA <= 32) ? tsg::ts_gemm_kernel<Int4Fmt, (N_MMA <= 32 ? N_MMA : 16), true, DBUF>
                                            : tsg::ts_gemm_kernel<Int4Fmt, N_MMA, false, DBUF>;

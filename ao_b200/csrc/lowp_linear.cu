@@ -13,8 +13,7 @@
 // scales go smem -> TMEM with tcgen05.cp.  Epilogue: TMEM -> registers -> scale/bias -> bf16.
 // Persistent stream-K (streamk.cuh): (tile, K-chunk) units split evenly over the CTAs; tiles shared by several
 // CTAs are finished by their owner CTA from the contributors' published 32-bit partials in CTA order
-// (deterministic; int32 for int8: stays exact).  The TMA producer also runs an L2 prefetch of the weight
-// chunks ahead of the shared-memory ring (the weight stream depends on nothing).
+// (deterministic; int32 for int8: stays exact).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -61,7 +60,6 @@ struct Params {
   int32_t* i32_out;       // raw int32 accumulators [M, N] (ao_int8_mm_i32)
   float* ws_partial;      // [grid][N_MMA*128] 32-bit partials (int32 bits for int8): CTA b's CONTRIB partial
   unsigned int* ws_flag;  // [grid] CTA b's partial is published (streamk.cuh)
-  int prefetch;           // weight chunks of L2 prefetch ahead of the ring (0 = none)
   int M, N, K;            // K in ELEMENTS
   int n_tiles, m_blocks, KT;  // KT = chunks of 128 K-bytes
   int sf_col_blocks_w;    // number of 4-wide scale column blocks per row block (blocked layout)
@@ -158,28 +156,11 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               : "memory");
         }
       };
-      auto prefetch_w = [&](int i) {
-        const int n_tile = tile_of(i) % p.n_tiles, kc = kc_of(i);
-        tma_prefetch_l2_2d(&tm_w, kc * KB, n_tile * ROWS);
-        if (C::BLOCK_SCALED)
-          bulk_prefetch_l2(w_sf + ((size_t)n_tile * p.sf_col_blocks_w + (size_t)kc * C::SF_TILES) * 512, C::SF_BYTES);
-      };
       const int pre = nunits < S ? nunits : S;
       for (int i = 0; i < pre; ++i) {
         if (elect_one()) issue_w(i);   // weights never depend on the previous kernel
         __syncwarp();
       }
-      // HBM -> L2 of the chunks behind the first ring-full (no shared memory needed): under PDL this runs while the
-      // previous kernel is still finishing
-      int pf = pre;
-      auto prefetch_to = [&](int upto) {
-        if (upto > nunits) upto = nunits;
-        for (; pf < upto; ++pf) {
-          if (elect_one()) prefetch_w(pf);
-          __syncwarp();
-        }
-      };
-      if (p.prefetch > 0) prefetch_to(pre + p.prefetch);
       pdl_wait();
       for (int i = 0; i < pre; ++i) {
         if (elect_one()) issue_x(i);
@@ -192,7 +173,6 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           issue_x(i);
         }
         __syncwarp();
-        if (p.prefetch > 0) prefetch_to(i + 1 + p.prefetch);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -409,7 +389,6 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   p.i32_out = i32_out;
   p.ws_flag = reinterpret_cast<unsigned int*>(ws);
   p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_PARTIAL_OFF);
-  p.prefetch = ts_prefetch();
   p.M = M; p.N = N; p.K = K;
   p.n_tiles = ceil_div(N, ROWS);
   p.m_blocks = ceil_div(M, N_MMA);

@@ -39,11 +39,6 @@ struct Nvfp4Fmt {
                  "l"(src), "r"(1024), "r"(smem_u32(bar))
                  : "memory");
   }
-  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p,
-                                                    int n_tile, int kc) {
-    tma_prefetch_l2_2d(tm_w, kc * 64, n_tile * ROWS);
-    bulk_prefetch_l2(p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512, 1024);
-  }
   // k-half h of row r: bytes 32h..32h+31 (k 64h..64h+63) and the four block scales of blocked tile h
   __device__ static __forceinline__ void dequant_half(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
                                                       int h, uint32_t (&out)[32]) {

@@ -17,21 +17,22 @@
 //                  in TMEM, so it overlaps the next segment's MMAs -- bias / scales, store or publish): the
 //                  warpgroup that dequantised a segment's last chunk finishes the segment after its NEXT chunk,
 //                  when the accumulator is long complete, so nothing ever blocks on the tensor pipe mid-stream
-//       WG3: warp 12 weight TMA producer (never waits for the previous kernel; also runs the L2 prefetch of the
-//                  chunks ahead of the ring), warp 14 activation TMA producer (after griddepcontrol.wait),
-//                  warp 13 MMA issuer
-//   * the weight stream is what the kernel is made of, and it depends on nothing: the producer issues
-//     cp.async.bulk.prefetch.tensor (HBM -> L2, no shared memory needed) `prefetch` chunks ahead of the ring, so
-//     the ring's loads are L2 hits (a 80 KB ring covers the L2 round trip several times over, not the DRAM one),
-//     and a CTA that is resident under the previous kernel pulls its first chunks into L2 while it waits for its
-//     activations
+//       WG3: warps 12 and 15 weight TMA producers (alternate chunks; never wait for the previous kernel), warp 14
+//                  activation TMA producer (after griddepcontrol.wait), warp 13 MMA issuer
+//   * the weight stream is what the kernel is made of, and it depends on nothing: a CTA that is resident under the
+//     previous kernel (PDL) fills its ring while it waits for its activations.  (An L2 prefetch ahead of the ring --
+//     cp.async.bulk.prefetch.tensor -- was measured neutral to slightly negative and removed: profiles/r02_call_b.log)
 //   * single-thread roles are WARP-UNIFORM loops with only the tcgen05 / TMA / mbarrier instruction under elect.sync
 //     (warp index through __shfl_sync so the compiler knows it is uniform): with a loop under `lane == 0` ptxas wraps
 //     every UTCHMMA / UTMALDG in an elect-broadcast loop and one thread issues an MMA only every ~52 cycles instead
 //     of ~20, the tensor pipe's own floor for M128 N16 K16 (scripts/mma_microbench7.cu)
-//   * the issuer does ONE wait and ONE commit per chunk: the activation slot of a chunk shares the index and the
-//     barriers of the chunk's TMEM A stage (afull = 4 dequant-warp arrivals + the activation tile's TMA transaction
-//     bytes; one tcgen05.commit on aempty frees both).  A-stage barriers are PAIRS per stage (see below)
+//   * the issuer does ONE wait and ONE commit per chunk: chunk i owns "chunk slot" i % X_SLOTS = its activation
+//     tile in shared memory plus a barrier pair (cfull = 4 dequant-warp arrivals + the activation tile's TMA
+//     transaction bytes; one tcgen05.commit on cempty says "the MMAs of chunk i are done": the activation slot is
+//     free for chunk i + X_SLOTS and the TMEM A stage i % A_STAGES for chunk i + A_STAGES).  The activation ring is
+//     DEEPER than the TMEM A ring on purpose: an activation tile can only be requested when its slot frees, its TMA
+//     load queues behind the weight boxes already in the SM's TMA unit, and the MMA of its chunk cannot issue before
+//     it lands -- with the rings tied together (round 1: 3 + 3) that latency, not dequant or HBM, set the chunk rate
 //   * the CTA's last segment is on the kernel's critical path: when it is an OWNER segment with more than 8 token
 //     columns, all four warpgroups share the gather (each takes every fourth group of 8 columns)
 //   * PDL: griddepcontrol.launch_dependents at start; only activations / outputs / workspace wait
@@ -51,7 +52,7 @@ constexpr int KCHUNK = 128;
 constexpr int W_BYTES = ROWS * KCHUNK / 2;  // 8 KiB of 4-bit weights per chunk
 constexpr int AUX_BYTES = 2048;             // scales per chunk (<= 2 KiB), 1 KiB aligned slot
 constexpr int A_COLS = 64;                  // TMEM columns of one bf16 A stage (128 k / 2)
-constexpr int DEQ_WGS = 3, DEQ_WARPS = 4 * DEQ_WGS, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14;
+constexpr int DEQ_WGS = 3, DEQ_WARPS = 4 * DEQ_WGS, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14, TMA_WARP1 = 15;
 constexpr int WSTAGE_BYTES = W_BYTES + AUX_BYTES;  // one weight stage: packed nibbles + scales
 constexpr int NUM_THREADS = 16 * 32;
 
@@ -62,14 +63,17 @@ struct Cfg {
   static constexpr int TMEM_COLS = N_MMA <= 64 ? 256 : 512;
   static constexpr int D_COLS = DBUF * N_MMA;
   static constexpr int A_COL0 = D_COLS <= 64 ? 64 : (D_COLS <= 128 ? 128 : 256);
-  static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4; also the depth of the activation ring
-  static constexpr int BUDGET = N_MMA <= 64 ? 104 * 1024 : 172 * 1024;
-  // weight stages (8, 8, 6 or 5).  A stage is consumed by whichever warpgroup its chunk belongs to; a consumer can
+  static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4 TMEM A stages
+  // chunk slots = depth of the activation ring (see the header): 6 x 4 / 8 KB for the decode sizes
+  static constexpr int X_SLOTS = N_MMA <= 32 ? 6 : (N_MMA <= 64 ? 3 : 4);
+  static constexpr int BUDGET = N_MMA <= 64 ? 110 * 1024 : 172 * 1024;
+  // weight stages (8, 6, 6 or 4).  A stage is consumed by whichever warpgroup its chunk belongs to; a consumer can
   // never be two phases away from the barrier it waits on (chunk i - STAGES was consumed before chunk i - 3 could
   // be stored, chunk i + STAGES cannot be issued before chunk i is consumed), so parity waits do not alias
-  static constexpr int STAGES = (BUDGET - A_STAGES * X_BYTES) / WSTAGE_BYTES;
+  static constexpr int STAGES_RAW = (BUDGET - X_SLOTS * X_BYTES) / WSTAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW >= 6 ? (STAGES_RAW & ~1) : STAGES_RAW;   // even when there is room: two producers
   static constexpr int X_OFF = STAGES * WSTAGE_BYTES;
-  static constexpr int BAR_OFF = X_OFF + A_STAGES * X_BYTES;
+  static constexpr int BAR_OFF = X_OFF + X_SLOTS * X_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)BAR_OFF + 1024 + 1024;
   __host__ __device__ static constexpr int d_col(int buf) { return buf * N_MMA; }
 };
@@ -85,8 +89,8 @@ struct Params {
   int M, N, N_out, K, group_size;
   int n_tiles, m_blocks, KT;   // KT = K/128
   int aux_col_blocks;
-  int prefetch;  // chunks of L2 prefetch ahead of the shared-memory ring (0 = none)
-  int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 2 = skip MMAs, 4 = no activation loads after the first ring-full
+  int producers; // weight TMA producer warps (1 or 2)
+  int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs, 4 = no activation loads after the first ring-full
   unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
 };
 
@@ -118,7 +122,6 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
 
 // Fmt policy:
 //   static void issue_w(tm_w, tm_aux, p, w smem dst, aux smem dst, full barrier, n_tile, kc, policy)  (one thread)
-//   static void prefetch_w(tm_w, tm_aux, p, n_tile, kc)                                              (one thread)
 //   static uint32_t w_tx_bytes(p)
 //   static void dequant_half(p, w smem, aux smem, row r, half h, out[32])   (128 threads; out[c] = bf16x2 of
 //                                                                            k = 64h + 2c, 64h + 2c + 1)
@@ -130,17 +133,19 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   using C = Cfg<N_MMA, DBUF>;
   constexpr int S = C::STAGES;
   constexpr int T = C::A_STAGES;
+  constexpr int SX = C::X_SLOTS;
+  static_assert(SX >= T, "a chunk slot must outlive its TMEM A stage");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* wfull = bars;             // [S]   weight TMA transaction
   uint64_t* sempty = wfull + S;       // [S]   4 dequant warps (the chunk's warpgroup) have the weights in registers
-  // A-stage barriers come in PAIRS per stage (use k = chunk / T of the stage goes to barrier k & 1, phase
-  // k >> 1): with T odd consecutive uses of a stage belong to different warpgroups, and a parity
-  // wait by a party that skips every other phase would alias; per pair every waiter sees every phase.
-  uint64_t* afull = sempty + S;       // [T][2] 4 dequant warps (A stage stored) + activation TMA (arrive.expect_tx)
-  uint64_t* aempty = afull + 2 * T;   // [T][2] MMA commit: A stage and activation slot both free
-  uint64_t* dfull = aempty + 2 * T;   // [2]   accumulator of a segment complete
+  // chunk-slot barriers (slot c = chunk % SX, use u = chunk / SX = phase u).  Waiters: the issuer and the activation
+  // producer visit every chunk in order; a dequant warpgroup looks at cempty of chunk i - T, which is either the
+  // barrier's current phase or the one just completed (later uses of the slot need chunks > i): no parity aliasing.
+  uint64_t* cfull = sempty + S;       // [SX] 4 dequant warps (A stage stored) + activation TMA (arrive.expect_tx)
+  uint64_t* cempty = cfull + SX;      // [SX] MMA commit: the chunk's MMAs are done
+  uint64_t* dfull = cempty + SX;      // [2]   accumulator of a segment complete
   uint64_t* dempty = dfull + 2;       // [2]   the 4 warps of the warpgroup that ran the segment's epilogue
   uint64_t* dlast = dempty + 2;       // [1]   accumulator of the CTA's LAST segment complete (single phase: any warp
                                       //       may wait on it without having followed the dfull phases)
@@ -160,6 +165,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       p.timeline[(size_t)b * 16 + e] = gt;
     }
   };
+  // fine-grained per-chunk stamps of CTA 0 (clock64: one SM, comparable across its warps), chunks FS0 .. FS0+7:
+  // 0 weights requested, 1 weights seen landed, 2 weight stage handed back, 3 A stage stored (cfull), 4 issuer saw the
+  // chunk complete, 5 MMAs issued + committed, 6 dequant saw the A stage free again
+  constexpr int FS0 = 16;
+  auto fstamp = [&](int i, int e) {
+    if (TL && p.timeline && b == 0 && i >= FS0 && i < FS0 + 8) p.timeline[100 * 16 + (i - FS0) * 8 + e] = (unsigned long long)clock64();
+  };
   if (threadIdx.x == 0) stamp(0);
   const long long U = (long long)p.n_tiles * p.m_blocks * p.KT;
   const int u0 = streamk::unit_begin(b, U, G), u1 = streamk::unit_begin(b + 1, U, G);
@@ -171,9 +183,9 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_init(&wfull[i], 1);
       mbar_init(&sempty[i], 4);
     }
-    for (int i = 0; i < 2 * T; ++i) {
-      mbar_init(&afull[i], 5);
-      mbar_init(&aempty[i], 1);
+    for (int i = 0; i < SX; ++i) {
+      mbar_init(&cfull[i], 5);
+      mbar_init(&cempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&dfull[i], 1);
@@ -353,32 +365,49 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       }
     };
 
-    // ring positions of chunk i = wg, wg + 3, ... kept incrementally (the integer pipe is busy enough here)
-    int s = wg % S, sph = 0, t = wg % T, k = wg / T;
+    // ring positions of chunk i = wg, wg + 3, ... kept incrementally (the integer pipe is busy enough here):
+    // weight stage s (phase sph), TMEM A stage t, chunk slot c, and the slot / phase of chunk i - T (ec, eph)
+    int s = wg % S, sph = (wg / S) & 1, t = wg % T, c = wg % SX;
+    // chunk wg - T: when negative it stands for "the lap before the first" (parity 1; never waited on)
+    int ec = wg >= T ? (wg - T) % SX : wg - T + SX, eph = wg >= T ? ((wg - T) / SX) & 1 : 1;
     for (int i = wg; i < nunits; i += DEQ_WGS) {
       const uint32_t st = smem_u32(smem + (size_t)s * WSTAGE_BYTES);
       const uint32_t a_t = lane_taddr + C::A_COL0 + t * A_COLS;
       mbar_wait(&wfull[s], sph);
       if (i == 0 && warp == 0 && lane == 0) stamp(3);
+      if (q4 == 0 && lane == 0) fstamp(i, 1);
       // the row in two 64-k halves (32 registers of output each): half 0 is computed before the A stage is
       // known to be free, so the wait overlaps its arithmetic
       uint32_t out[32];
+      if (p.flags & 1) {   // bring-up: no dequant arithmetic, no TMEM stores (garbage results)
+        if (i >= T) mbar_wait(&cempty[ec], eph);
+        __syncwarp();
+        if (elect_one()) { mbar_arrive(&sempty[s]); mbar_arrive(&cfull[c]); }
+      } else {
       Fmt::dequant_half(p, st, st + W_BYTES, r, 0, out);
-      if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);  // MMAs of chunk i - T are done
+      if (i >= T) mbar_wait(&cempty[ec], eph);  // MMAs of chunk i - T are done: A stage t is free
+      if (q4 == 0 && lane == 0) fstamp(i, 6);
       tc_fence_after();
       tmem_st_x32(a_t, out);   // source registers are consumed at issue: no tcgen05.wait::st before reusing them
       Fmt::dequant_half(p, st, st + W_BYTES, r, 1, out);
       __syncwarp();
       if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
+      if (q4 == 0 && lane == 0) fstamp(i, 2);
       tmem_st_x32(a_t + 32, out);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (elect_one()) mbar_arrive(&afull[t * 2 + (k & 1)]);
+      if (elect_one()) mbar_arrive(&cfull[c]);
+      if (q4 == 0 && lane == 0) fstamp(i, 3);
+      }
       s += DEQ_WGS;
       if (s >= S) { s -= S; sph ^= 1; }
       t += DEQ_WGS;
-      while (t >= T) { t -= T; ++k; }
+      while (t >= T) t -= T;
+      c += DEQ_WGS;
+      if (c >= SX) c -= SX;
+      ec += DEQ_WGS;
+      if (ec >= SX) { ec -= SX; eph ^= 1; }
       run_epilogues(i);   // segments this warpgroup's EARLIER chunks completed: their accumulators are long done
     }
     run_epilogues(nunits);   // whatever is left of the segments before the last one
@@ -401,49 +430,43 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (warp == (wg << 2) && lane == 0) stamp(7);
     }
   } else if (warp >= TMA_WARP) {
-    if (warp == TMA_WARP) {
-      // ---------------------------------------------------------- weight producer.  Weights never depend on the
-      // previous kernel: no griddepcontrol.wait on this path.
+    if (warp == TMA_WARP || (warp == TMA_WARP1 && p.producers == 2)) {
+      // ---------------------------------------------------------- weight producers.  Weights never depend on the
+      // previous kernel: no griddepcontrol.wait on this path.  One thread gets a TMA box pair out every ~600
+      // cycles (scripts/stream_microbench.cu: one producer warp 4.4-4.8 TB/s, two 5.1-6.0 TB/s), so with
+      // p.producers == 2 warps 12 and 15 take alternate chunks (STAGES is even: a stage always belongs to the same
+      // producer, which therefore sees every phase of its sempty barrier)
       const uint64_t pol_w = policy_evict_first();
-      int s = 0, sph = 0, kc = kc_of(0), n_tile = tile_of(0) % p.n_tiles;
-      // L2 prefetch cursor (chunk index and its coordinates); starts right behind the first ring-full
-      int pf_i = -1, pf_kc = 0, pf_nt = 0;
-      const int primed = S < nunits ? S : nunits;
-      for (int i = 0; i < nunits; ++i) {
+      const int np = p.producers, pi = (warp == TMA_WARP) ? 0 : 1;
+      int s = pi, sph = 0, kc = kc_of(0) + pi, n_tile = tile_of(0) % p.n_tiles;
+      if (kc >= p.KT) { kc -= p.KT; if (++n_tile == p.n_tiles) n_tile = 0; }
+      for (int i = pi; i < nunits; i += np) {
         if (i >= S) mbar_wait(&sempty[s], sph ^ 1);
         if (elect_one()) {
           uint8_t* st = smem + (size_t)s * WSTAGE_BYTES;
           mbar_expect_tx(&wfull[s], Fmt::w_tx_bytes(p));
           Fmt::issue_w(&tm_w, &tm_aux, p, st, st + W_BYTES, &wfull[s], n_tile, kc, pol_w);
+          fstamp(i, 0);
         }
         __syncwarp();
-        if (++s == S) { s = 0; sph ^= 1; }
-        if (++kc == p.KT) { kc = 0; if (++n_tile == p.n_tiles) n_tile = 0; }
-        // once the ring is primed, keep the L2 prefetch `prefetch` chunks ahead of the ring's loads
-        if (p.prefetch > 0 && i + 1 >= primed) {
-          if (pf_i < 0) { pf_i = i + 1; pf_kc = kc; pf_nt = n_tile; }
-          int upto = i + 1 + p.prefetch;
-          if (upto > nunits) upto = nunits;
-          for (; pf_i < upto; ++pf_i) {
-            if (elect_one()) Fmt::prefetch_w(&tm_w, &tm_aux, p, pf_nt, pf_kc);
-            __syncwarp();
-            if (++pf_kc == p.KT) { pf_kc = 0; if (++pf_nt == p.n_tiles) pf_nt = 0; }
-          }
-        }
+        s += np;
+        if (s >= S) { s -= S; sph ^= 1; }
+        kc += np;
+        if (kc >= p.KT) { kc -= p.KT; if (++n_tile == p.n_tiles) n_tile = 0; }
       }
     } else if (warp == XTMA_WARP) {
       // ---------------------------------------------------------- activation producer
       const uint64_t pol_x = policy_evict_last();
       pdl_wait();   // activations are the previous kernel's output
       if (lane == 0) stamp(2);
-      int t = 0, k = 0, kc = kc_of(0), tile = tile_of(0);
+      int c = 0, cph = 1, kc = kc_of(0), tile = tile_of(0);   // cph: parity of the slot's PREVIOUS use
       for (int i = 0; i < nunits; ++i) {
-        uint64_t* full = &afull[t * 2 + (k & 1)];
-        if (k >= 1) mbar_wait(&aempty[t * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1);
+        uint64_t* full = &cfull[c];
+        if (i >= SX) mbar_wait(&cempty[c], cph);   // MMAs of chunk i - SX are done: the slot is free
         if (elect_one()) {
-          uint8_t* xs = smem + C::X_OFF + (size_t)t * C::X_BYTES;
+          uint8_t* xs = smem + C::X_OFF + (size_t)c * C::X_BYTES;
           const int m0 = (tile / p.n_tiles) * N_MMA, k0 = kc * KCHUNK;
-          if ((p.flags & 4) && i >= T) {
+          if ((p.flags & 4) && i >= SX) {
             mbar_arrive(full);   // bring-up: no activation loads after the first ring-full (garbage results)
           } else {
             mbar_expect_tx(full, C::X_BYTES);
@@ -452,14 +475,14 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           }
         }
         __syncwarp();
-        if (++t == T) { t = 0; ++k; }
+        if (++c == SX) { c = 0; cph ^= 1; }
         if (++kc == p.KT) { kc = 0; ++tile; }
       }
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);
       const uint32_t x0 = smem_u32(smem + C::X_OFF);
-      int c = 0, t = 0, k = 0;
+      int c = 0, t = 0, cs = 0, cph = 0;   // chunk, its A stage, its slot and the slot's phase parity
       for (int seg = 0; seg < walk.nseg; ++seg) {
         const int cnt = walk.seg_count(seg);
         const int buf = seg % DBUF, ph = (seg / DBUF) & 1;
@@ -467,23 +490,26 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         const uint32_t d_t = tmem_base + C::d_col(buf);
         uint32_t acc = 0;   // first MMA of the segment overwrites the accumulator
         for (const int c_end = c + cnt; c < c_end; ++c) {
-          mbar_wait(&afull[t * 2 + (k & 1)], (k >> 1) & 1);
+          mbar_wait(&cfull[cs], cph);
           tc_fence_after();
           if (elect_one()) {
             if (c == 0) stamp(4);
-            const uint32_t xb = x0 + t * C::X_BYTES;
+            fstamp(c, 4);
+            const uint32_t xb = x0 + cs * C::X_BYTES;
             const uint32_t a_t = tmem_base + C::A_COL0 + t * A_COLS;
             const uint64_t b_lo = umma_desc_k_sw128(xb), b_hi = umma_desc_k_sw128(xb + N_MMA * 128);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               if (!(p.flags & 2))   // bring-up: flag 2 skips the MMAs
                 mma_ts_f16(d_t, a_t + kk * 8, (kk < 4 ? b_lo : b_hi) + (uint64_t)((kk & 3) * 2), idesc, (kk == 0) ? acc : 1u);
-            tc_commit(&aempty[t * 2 + (k & 1)]);
+            tc_commit(&cempty[cs]);
+            fstamp(c, 5);
             if (c == nunits - 1) stamp(5);
           }
           __syncwarp();
           acc = 1u;
-          if (++t == T) { t = 0; ++k; }
+          if (++t == T) t = 0;
+          if (++cs == SX) { cs = 0; cph ^= 1; }
         }
         if (elect_one()) {
           tc_commit(&dfull[buf]);   // all MMAs of the segment have completed
@@ -534,7 +560,7 @@ inline int plan(Params& p, void* ws, size_t ws_bytes, const char* what, int* gri
   p.ws_flag = reinterpret_cast<unsigned int*>(ws);
   p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_PARTIAL_OFF);
   p.flags = ts_flags();
-  p.prefetch = ts_prefetch();
+  p.producers = (ts_producers() == 1 || (Cfg<N_MMA>::STAGES & 1)) ? 1 : 2;
   *grid_out = grid;
   return AO_OK;
 }

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 torch.ops.load_library(os.path.join(ROOT, "ao_b200", "lib", "ao_b200_torch.so"))
 ops = torch.ops.ao_b200
 g = 32
-SLOT = (100 * 16) * 8
+SLOT = (100 * 16 + 64) * 8
 BASE = 20 << 20
 
 
@@ -24,7 +24,11 @@ def mk(N, K):
 
 
 def slot(ws, i):
-    return ws[BASE + i * SLOT: BASE + (i + 1) * SLOT].view(torch.int64).reshape(100, 16).cpu()
+    return ws[BASE + i * SLOT: BASE + i * SLOT + 100 * 16 * 8].view(torch.int64).reshape(100, 16).cpu()
+
+
+def fine(ws, i):
+    return ws[BASE + i * SLOT + 100 * 16 * 8: BASE + (i + 1) * SLOT].view(torch.int64).reshape(8, 8).cpu()
 
 
 Ms = (1, 32) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split(','))
@@ -56,4 +60,10 @@ for M in Ms:
                     continue
                 parts.append(f"{names[e]} {col.min():.1f}/{col.median():.1f}/{col.max():.1f}")
             print(f"   {nm:4s}" + "  ".join(parts))
+        f = fine(ws, 0) if ua[:, 0].min() >= ub[:, 0].min() else fine(ws, 1)   # the later kernel's CTA 0
+        if int(f[0, 0]) > 0:
+            base = int(f[0, 0])
+            print("   CTA 0, chunks 16..23 (SM cycles since chunk 16 was requested): requested / landed / stage back / A stored / issuer saw / committed / A free")
+            for c in range(8):
+                print("     chunk %2d: " % (16 + c) + "  ".join("%6d" % (int(f[c, e]) - base) if int(f[c, e]) > 0 else "     -" for e in range(7)))
         print(f"   launch-to-launch: {(int(second[:, 9].max()) - int(first[:, 9].max())) / 1e3:.2f} us  (end of k+1 minus end of k)")
