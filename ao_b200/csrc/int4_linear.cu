@@ -13,7 +13,7 @@
 //   bits [16+4e, ..) = q[n, k0 + 8e + 1]
 // so one row's 128 k of a k-tile are the 64 contiguous bytes of lanes 4*(n%8)..+3, a 128-row chunk is
 // 16 runs of 512 B, fetched by ONE 3-D TMA box {32 words, 4 row-pairs, 16 n8-tiles} with 128-byte
-// swizzle -- which also makes the per-thread 16-byte ld.shared of "its" row bank-conflict free.
+// swizzle -- which makes the per-thread 16-byte ld.shared.v4 of "its" row bank-conflict free (Int4Fmt::load_row).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -48,41 +48,50 @@ struct Int4Fmt {
     tma_load_3d(w_dst, tm_w, bar, 0, 4 * kc, n_tile * (ROWS / 8), policy);
     tma_load_2d(aux_dst, tm_sz, bar, n_tile * ROWS, (kc * KCHUNK) / p.group_size, policy);
   }
-  // thread r (= TMEM lane = weight row of the tile), k-half h: 32 packed bytes + up to 2 (s,z) pairs -> 32 bf16x2
-  // (out[c] = k pair 64h + 2c, 64h + 2c + 1).  The row's 64 bytes are four 16-byte lane words (tinygemm word
-  // wd = k 32wd..32wd+31 sits at byte 4wd of each); half h needs words 2h, 2h+1 = the 8 bytes at +8h of each.
-  __device__ static __forceinline__ void dequant_half(const tsg::Params& p, uint32_t w_smem, uint32_t aux_smem, int r,
-                                                      int h, uint32_t (&out)[32]) {
+  // One weight row of the chunk in registers: the row's 64 bytes are the four 16-byte lane words of its n8 group
+  // (tinygemm word wd of lane word i holds k = 32wd + 2i + 8e + {0,1}), plus the (s, z) pair of each 32-k word.
+  struct Raw {
+    uint4 v[4];
+    uint32_t sz[4];
+  };
+  // thread r (= TMEM lane = weight row of the tile): 4 x ld.shared.v4 through the TMA 128-byte swizzle -- per
+  // quarter-warp the eight rows hit eight different 16-byte bank groups: conflict-free (the half-row ld.shared.v2
+  // of round 1 was 2-way conflicted: profiles/r01_int4_final_ncu_full.csv) -- and 4 x ld.shared.b32 of (s, z)
+  __device__ static __forceinline__ void load_row(const tsg::Params& p, uint32_t w_smem, uint32_t aux_smem, int r, Raw& raw) {
+    const int gshift = p.group_size == 32 ? 0 : (p.group_size == 64 ? 1 : 2);  // 32-k word -> group of the chunk
+#pragma unroll
+    for (int w = 0; w < 4; ++w) raw.sz[w] = tsg::lds32(aux_smem + r * 4 + (w >> gshift) * 512);
     const uint32_t row_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u;
-    const int gshift = p.group_size == 32 ? 0 : (p.group_size == 64 ? 1 : 2);  // word -> group
-    uint32_t magic = 0x43004300u;
-    asm volatile("" : "+r"(magic));  // keep it in a register
-    uint2 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t off = row_off + i * 16;
-      v[i] = tsg::lds64(w_smem + (off ^ (((off >> 7) & 7) << 4)) + 8 * h);  // undo the TMA 128B swizzle
+      raw.v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 7) << 4)));  // undo the TMA 128B swizzle
     }
-    uint32_t sz[2];  // (s,z) of the group each 32-k word belongs to
+  }
+  __device__ static __forceinline__ void touch(const Raw& raw) {
 #pragma unroll
-    for (int w2 = 0; w2 < 2; ++w2) sz[w2] = tsg::lds32(aux_smem + r * 4 + ((2 * h + w2) >> gshift) * 512);
+    for (int i = 0; i < 4; ++i) asm volatile("" ::"r"(raw.v[i].x), "r"(raw.v[i].y), "r"(raw.v[i].z), "r"(raw.v[i].w));
+    asm volatile("" ::"r"(raw.sz[0]), "r"(raw.sz[1]), "r"(raw.sz[2]), "r"(raw.sz[3]));
+  }
+  // quarter q = the 32 k of tinygemm word q: out[c] = bf16x2 of k pair (32q + 2c, 32q + 2c + 1), c = i + 4e
+  __device__ static __forceinline__ void dequant_quarter(const tsg::Params&, const Raw& raw, int q, uint32_t (&out)[16]) {
+    uint32_t magic = 0x43004300u;
+    asm volatile("" : "+r"(magic));  // keep it in a register
+    const uint32_t sz = raw.sz[q];
+    const uint32_t s_bits = __byte_perm(sz, sz, 0x1010);
+    const uint32_t z_bits = __byte_perm(sz, sz, 0x3232);
+    const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
+    const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&z_bits);
 #pragma unroll
-    for (int w2 = 0; w2 < 2; ++w2) {
-      const uint32_t s_bits = __byte_perm(sz[w2], sz[w2], 0x1010);
-      const uint32_t z_bits = __byte_perm(sz[w2], sz[w2], 0x3232);
-      const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
-      const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&z_bits);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t word = q == 0 ? raw.v[i].x : q == 1 ? raw.v[i].y : q == 2 ? raw.v[i].z : raw.v[i].w;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t word = (w2 == 0) ? v[i].x : v[i].y;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // bf16x2 of 128+q = ((word >> 4e) & 0x000F000F) | 0x43004300 as ONE lop3 (the integer pipe is what
-          // bounds this kernel; C source compiles to two LOP3 because both constants want the immediate slot)
-          uint32_t m;
-          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(m) : "r"(word >> (4 * e)), "r"(0x000F000Fu), "r"(magic));
-          out[16 * w2 + i + 4 * e] = deq_pair(m, s2, z2);                         // k pair (64h+32w2+2i+8e, +1)
-        }
+      for (int e = 0; e < 4; ++e) {
+        // bf16x2 of 128+q = ((word >> 4e) & 0x000F000F) | 0x43004300 as ONE lop3 (C source compiles to two LOP3
+        // because both constants want the immediate slot)
+        uint32_t m;
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(m) : "r"(word >> (4 * e)), "r"(0x000F000Fu), "r"(magic));
+        out[i + 4 * e] = deq_pair(m, s2, z2);   // k pair (32q + 2i + 8e, +1)
       }
     }
   }

@@ -39,22 +39,35 @@ struct Nvfp4Fmt {
                  "l"(src), "r"(1024), "r"(smem_u32(bar))
                  : "memory");
   }
-  // k-half h of row r: bytes 32h..32h+31 (k 64h..64h+63) and the four block scales of blocked tile h
-  __device__ static __forceinline__ void dequant_half(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r,
-                                                      int h, uint32_t (&out)[32]) {
-    uint4 v[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const uint32_t off = (uint32_t)r * 64u + (2 * h + i) * 16;
-      v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 3) << 4)));  // undo the TMA 64B swizzle
-    }
+  // one weight row of the chunk: its 64 bytes (k 0..127, even k in the low nibble) and the 8 block scales
+  struct Raw {
+    uint4 v[4];
+    uint32_t sc[2];   // blocked tile h (k 64h..64h+63): four e4m3 scale bytes
+  };
+  __device__ static __forceinline__ void load_row(const tsg::Params&, uint32_t w_smem, uint32_t aux_smem, int r, Raw& raw) {
     const uint32_t sc_off = (uint32_t)(r & 31) * 16u + (uint32_t)(r >> 5) * 4u;
-    const uint32_t sc = tsg::lds32(aux_smem + 512 * h + sc_off);
+    raw.sc[0] = tsg::lds32(aux_smem + sc_off);
+    raw.sc[1] = tsg::lds32(aux_smem + 512 + sc_off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = (uint32_t)r * 64u + i * 16;
+      raw.v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 3) << 4)));  // undo the TMA 64B swizzle
+    }
+  }
+  __device__ static __forceinline__ void touch(const Raw& raw) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("" ::"r"(raw.v[i].x), "r"(raw.v[i].y), "r"(raw.v[i].z), "r"(raw.v[i].w));
+    asm volatile("" ::"r"(raw.sc[0]), "r"(raw.sc[1]));
+  }
+  // quarter q = bytes 16q..16q+15 of the row = k 32q..32q+31: out[c] = bf16x2 of k pair (32q + 2c, +1)
+  __device__ static __forceinline__ void dequant_quarter(const tsg::Params&, const Raw& raw, int q, uint32_t (&out)[16]) {
+    const uint4 v = raw.v[q];
+    const uint32_t sc = raw.sc[q >> 1] >> (16 * (q & 1));   // two scale bytes: blocks 2q, 2q + 1
     const uint32_t two120 = 0x7B807B80u;  // bf16x2 of 2^120
     const __nv_bfloat162 c120 = *reinterpret_cast<const __nv_bfloat162*>(&two120);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {  // word w = bytes 4w..4w+3 of the half = k 8w..8w+7; scale block = w/2
-      const uint32_t word = (w & 3) == 0 ? v[w >> 2].x : (w & 3) == 1 ? v[w >> 2].y : (w & 3) == 2 ? v[w >> 2].z : v[w >> 2].w;
+    for (int w = 0; w < 4; ++w) {  // word w = k 8w..8w+7 of the quarter; scale block = w/2
+      const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
       const uint32_t sb = (sc >> (8 * (w >> 1))) & 0xFFu;
       const uint32_t s_bits = ((sb << 4) + 0x3F00u) * 0x00010001u;  // bf16x2 of scale * 2^6
       const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);

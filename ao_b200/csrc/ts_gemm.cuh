@@ -9,8 +9,9 @@
 //     the CTAs; split tiles are finished by their OWNER CTA from the contributors' published partials
 //   * 16 warps in four warpgroups, 64 registers per thread, 256 TMEM columns, ~105 KB smem (two CTAs fit per SM,
 //     so the next linear's CTA is resident -- PDL -- and has its weights in flight while this one finishes):
-//       WG0..WG2 (warps 0-11): dequant, chunk i belongs to warpgroup i % 3: ld.shared -> unpack/scale in bf16x2,
-//                  one 64-k half row (32 registers) at a time -> tcgen05.st of the bf16 A operand into one of the
+//       WG0..WG2 (warps 0-11): dequant, chunk i belongs to warpgroup i % 3: the thread's weight row into registers
+//                  (conflict-free ld.shared.v4; the weight stage is handed back right away), unpack/scale in bf16x2
+//                  a quarter row (16 registers) at a time -> tcgen05.st.x16 of the bf16 A operand into one of the
 //                  TMEM A stages.  A chunk is a serial chain of waits (weights landed, A stage free, TMEM store
 //                  done) around ~400 instructions, so what counts is how many chunks are in flight per SM: three.
 //                  The same warpgroups run the epilogues (tcgen05.ld of a finished accumulator -- double-buffered
@@ -123,8 +124,9 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
 // Fmt policy:
 //   static void issue_w(tm_w, tm_aux, p, w smem dst, aux smem dst, full barrier, n_tile, kc, policy)  (one thread)
 //   static uint32_t w_tx_bytes(p)
-//   static void dequant_half(p, w smem, aux smem, row r, half h, out[32])   (128 threads; out[c] = bf16x2 of
-//                                                                            k = 64h + 2c, 64h + 2c + 1)
+//   struct Raw; static void load_row(p, w smem, aux smem, row r, Raw&)      (128 threads: one weight row each)
+//   static void touch(const Raw&)                                          (all of load_row's loads have returned)
+//   static void dequant_quarter(p, raw, q, out[16])                        (out[c] = bf16x2 of k = 32q + 2c, + 1)
 // TL = true compiles the per-CTA phase-timestamp instrumentation in (bring-up builds only).
 template <class Fmt, int N_MMA, bool TL = false, int DBUF = 2>
 __global__ void __launch_bounds__(NUM_THREADS, (N_MMA <= 64 ? 2 : 1))
@@ -376,29 +378,36 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_wait(&wfull[s], sph);
       if (i == 0 && warp == 0 && lane == 0) stamp(3);
       if (q4 == 0 && lane == 0) fstamp(i, 1);
-      // the row in two 64-k halves (32 registers of output each): half 0 is computed before the A stage is
-      // known to be free, so the wait overlaps its arithmetic
-      uint32_t out[32];
+      // the whole row into registers (16 + a few), then four quarters of 32 k -> 16 registers -> tcgen05.st.x16 each.
+      // The weight stage goes back to the producers as soon as the row is in registers; quarter 0 is computed before
+      // the A stage is known to be free, so that wait overlaps arithmetic.
       if (p.flags & 1) {   // bring-up: no dequant arithmetic, no TMEM stores (garbage results)
         if (i >= T) mbar_wait(&cempty[ec], eph);
         __syncwarp();
         if (elect_one()) { mbar_arrive(&sempty[s]); mbar_arrive(&cfull[c]); }
       } else {
-      Fmt::dequant_half(p, st, st + W_BYTES, r, 0, out);
-      if (i >= T) mbar_wait(&cempty[ec], eph);  // MMAs of chunk i - T are done: A stage t is free
-      if (q4 == 0 && lane == 0) fstamp(i, 6);
-      tc_fence_after();
-      tmem_st_x32(a_t, out);   // source registers are consumed at issue: no tcgen05.wait::st before reusing them
-      Fmt::dequant_half(p, st, st + W_BYTES, r, 1, out);
-      __syncwarp();
-      if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
-      if (q4 == 0 && lane == 0) fstamp(i, 2);
-      tmem_st_x32(a_t + 32, out);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (elect_one()) mbar_arrive(&cfull[c]);
-      if (q4 == 0 && lane == 0) fstamp(i, 3);
+        typename Fmt::Raw raw;
+        Fmt::load_row(p, st, st + W_BYTES, r, raw);
+        uint32_t out[16];
+        Fmt::dequant_quarter(p, raw, 0, out);
+        Fmt::touch(raw);   // every ld.shared of the row has returned (quarter 0 alone does not use all of them)
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
+        if (q4 == 0 && lane == 0) fstamp(i, 2);
+        if (i >= T) mbar_wait(&cempty[ec], eph);  // MMAs of chunk i - T are done: A stage t is free
+        if (q4 == 0 && lane == 0) fstamp(i, 6);
+        tc_fence_after();
+        tmem_st_x16(a_t, out);   // source registers are consumed at issue: no tcgen05.wait::st before reusing them
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          Fmt::dequant_quarter(p, raw, q, out);
+          tmem_st_x16(a_t + 16 * q, out);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&cfull[c]);
+        if (q4 == 0 && lane == 0) fstamp(i, 3);
       }
       s += DEQ_WGS;
       if (s >= S) { s -= S; sph ^= 1; }
