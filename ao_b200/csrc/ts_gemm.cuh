@@ -491,40 +491,60 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);
       const uint32_t x0 = smem_u32(smem + C::X_OFF);
-      int c = 0, t = 0, cs = 0, cph = 0;   // chunk, its A stage, its slot and the slot's phase parity
-      for (int seg = 0; seg < walk.nseg; ++seg) {
-        const int cnt = walk.seg_count(seg);
-        const int buf = seg % DBUF, ph = (seg / DBUF) & 1;
-        mbar_wait(&dempty[buf], ph ^ 1);
-        const uint32_t d_t = tmem_base + C::d_col(buf);
-        uint32_t acc = 0;   // first MMA of the segment overwrites the accumulator
-        for (const int c_end = c + cnt; c < c_end; ++c) {
-          mbar_wait(&cfull[cs], cph);
-          tc_fence_after();
-          if (elect_one()) {
-            if (c == 0) stamp(4);
-            fstamp(c, 4);
-            const uint32_t xb = x0 + cs * C::X_BYTES;
-            const uint32_t a_t = tmem_base + C::A_COL0 + t * A_COLS;
-            const uint64_t b_lo = umma_desc_k_sw128(xb), b_hi = umma_desc_k_sw128(xb + N_MMA * 128);
+      // The issuer shares its scheduler with three dequant warps, so every instruction it needs per chunk costs it
+      // issue slots it has to win: the chunk loop is unrolled over the X_SLOTS chunk slots, which makes the slot,
+      // its barriers, the activation descriptors and (X_SLOTS % A_STAGES == 0) the TMEM A stage compile-time
+      // constants -- one try_wait, eight UTCHMMA with immediate / uniform operands, one commit.
+      constexpr bool T_STATIC = (SX % T) == 0;
+      int c = 0, seg = 0, seg_end = walk.seg_count(0) - 1, t_dyn = 0;
+      uint32_t cph = 0;          // phase parity of the current lap over the chunk slots
+      uint32_t acc = 0;          // first MMA of a segment overwrites the accumulator
+      uint32_t d_t = tmem_base + C::d_col(0);
+      mbar_wait(&dempty[0], 1);  // (fresh barrier: returns at once)
+      while (c < nunits) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              if (!(p.flags & 2))   // bring-up: flag 2 skips the MMAs
-                mma_ts_f16(d_t, a_t + kk * 8, (kk < 4 ? b_lo : b_hi) + (uint64_t)((kk & 3) * 2), idesc, (kk == 0) ? acc : 1u);
-            tc_commit(&cempty[cs]);
-            fstamp(c, 5);
-            if (c == nunits - 1) stamp(5);
+        for (int j = 0; j < SX; ++j) {
+          if (c < nunits) {
+            mbar_wait(&cfull[j], cph);
+            tc_fence_after();
+            const uint32_t a_t = tmem_base + C::A_COL0 + (T_STATIC ? (j % T) : t_dyn) * A_COLS;
+            if (elect_one()) {
+              if (c == 0) stamp(4);
+              fstamp(c, 4);
+              const uint32_t xb = x0 + j * C::X_BYTES;
+              const uint64_t b_lo = umma_desc_k_sw128(xb), b_hi = umma_desc_k_sw128(xb + N_MMA * 128);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                if (!(p.flags & 2))   // bring-up: flag 2 skips the MMAs
+                  mma_ts_f16(d_t, a_t + kk * 8, (kk < 4 ? b_lo : b_hi) + (uint64_t)((kk & 3) * 2), idesc, (kk == 0) ? acc : 1u);
+              tc_commit(&cempty[j]);
+              fstamp(c, 5);
+              if (c == nunits - 1) stamp(5);
+            }
+            __syncwarp();
+            acc = 1u;
+            if (!T_STATIC) { if (++t_dyn == T) t_dyn = 0; }
+            if (c == seg_end) {
+              // segment complete: its accumulator is ready once these MMAs are; move to the next buffer
+              const int buf = seg % DBUF;
+              if (elect_one()) {
+                tc_commit(&dfull[buf]);
+                if (seg == seg_last) tc_commit(dlast);
+              }
+              __syncwarp();
+              ++seg;
+              if (seg < walk.nseg) {
+                seg_end += walk.seg_count(seg);
+                const int nb = seg % DBUF;
+                mbar_wait(&dempty[nb], ((seg / DBUF) & 1) ^ 1);   // epilogue of segment seg - DBUF done
+                d_t = tmem_base + C::d_col(nb);
+                acc = 0;
+              }
+            }
+            ++c;
           }
-          __syncwarp();
-          acc = 1u;
-          if (++t == T) t = 0;
-          if (++cs == SX) { cs = 0; cph ^= 1; }
         }
-        if (elect_one()) {
-          tc_commit(&dfull[buf]);   // all MMAs of the segment have completed
-          if (seg == seg_last) tc_commit(dlast);
-        }
-        __syncwarp();
+        cph ^= 1;
       }
     }
     if (coop) coop_help(3);
