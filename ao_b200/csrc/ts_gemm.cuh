@@ -296,7 +296,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   };
   // cooperative OWNER finish of the last segment: every warpgroup takes every fourth group of 8 token columns
   auto coop_help = [&](int helper) {
-    pdl_wait();   // outputs and workspace belong to the previous kernel until it has completed (long past by now)
+    // (every warp has executed griddepcontrol.wait by now -- at a point where it had nothing else to do, see the roles)
     while (!mbar_try_wait(dlast, 0)) __nanosleep(32);   // the producers get here early: do not steal issue slots
     tc_fence_after();
     if (helper == 0 && (warp & 3) == 0 && lane == 0) stamp(6);
@@ -394,7 +394,13 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         __syncwarp();
         if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
         if (q4 == 0 && lane == 0) fstamp(i, 2);
-        if (i >= T) mbar_wait(&cempty[ec], eph);  // MMAs of chunk i - T are done: A stage t is free
+        if (i >= T) {
+          // the first T chunks were dequantised under the previous kernel; from here on the warpgroup needs MMAs of
+          // THIS kernel, which need its activations, which need the previous kernel: the dependency wait costs nothing
+          // here, and every later use of outputs / workspace by this warp is covered
+          if (!waited_prev) { pdl_wait(); waited_prev = true; }
+          mbar_wait(&cempty[ec], eph);  // MMAs of chunk i - T are done: A stage t is free
+        }
         if (q4 == 0 && lane == 0) fstamp(i, 6);
         tc_fence_after();
         tmem_st_x16(a_t, out);   // source registers are consumed at issue: no tcgen05.wait::st before reusing them
@@ -419,6 +425,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (ec >= SX) { ec -= SX; eph ^= 1; }
       run_epilogues(i);   // segments this warpgroup's EARLIER chunks completed: their accumulators are long done
     }
+    if (!waited_prev) { pdl_wait(); waited_prev = true; }
     run_epilogues(nunits);   // whatever is left of the segments before the last one
     // ---- the CTA's last segment
     if (coop) {
@@ -463,6 +470,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         kc += np;
         if (kc >= p.KT) { kc -= p.KT; if (++n_tile == p.n_tiles) n_tile = 0; }
       }
+      pdl_wait();   // idle from here on: be ready to help with the last segment's outputs
     } else if (warp == XTMA_WARP) {
       // ---------------------------------------------------------- activation producer
       const uint64_t pol_x = policy_evict_last();
@@ -495,6 +503,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       // issue slots it has to win: the chunk loop is unrolled over the X_SLOTS chunk slots, which makes the slot,
       // its barriers, the activation descriptors and (X_SLOTS % A_STAGES == 0) the TMEM A stage compile-time
       // constants -- one try_wait, eight UTCHMMA with immediate / uniform operands, one commit.
+      pdl_wait();   // its first MMA needs the activations anyway
       constexpr bool T_STATIC = (SX % T) == 0;
       int c = 0, seg = 0, seg_end = walk.seg_count(0) - 1, t_dyn = 0;
       uint32_t cph = 0;          // phase parity of the current lap over the chunk slots
@@ -547,7 +556,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         cph ^= 1;
       }
     }
-    if (coop) coop_help(3);
+    if (coop) {
+      if (warp == TMA_WARP1 && p.producers != 2) pdl_wait();
+      coop_help(3);
+    }
   }
 
   __syncwarp();
