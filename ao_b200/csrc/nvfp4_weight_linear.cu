@@ -86,9 +86,9 @@ struct Nvfp4Fmt {
 };
 
 template <int N_MMA>
-static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, const uint8_t* wq, const uint8_t* w_sf,
-                     const float* b_pts, int N, const uint16_t* bias, uint16_t* y, void* ws, size_t ws_bytes,
-                     cudaStream_t stream) {
+static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, int K, const uint8_t* wq, const uint8_t* w_sf,
+                     const float* b_pts, int b_pts_per_row, int N, const uint16_t* bias, uint16_t* y, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
   using C = tsg::Cfg<N_MMA>;
   CUtensorMap tm_w, tm_x;
   {
@@ -100,7 +100,7 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint64_t str[1] = {(uint64_t)ldx * 2};
     const uint32_t box[2] = {64, (uint32_t)N_MMA};
     int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -109,6 +109,7 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.row_scale = x_scale;
   p.out_scale = b_pts;
+  p.out_scale_per_row = b_pts_per_row;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.aux_base = w_sf;
   p.aux_col_blocks = ceil_div(K / 16, 4);
@@ -127,12 +128,16 @@ static int launch_tc(const uint16_t* x, const float* x_scale, int M, int K, cons
 
 // per-token e4m3 "fake quantisation": x -> bf16(e4m3(x / s)) and s = f32(bf16(amax/448)); the bf16 values
 // are exactly the e4m3 codes Float8Tensor.from_hp(x, PerRow()) would store (quant_primitives.py:2172-2287).
-__global__ void __launch_bounds__(256) fp8_fakequant_rowwise_kernel(const __nv_bfloat16* __restrict__ x, int K,
+__global__ void __launch_bounds__(256) fp8_fakequant_rowwise_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int K,
                                                                     __nv_bfloat16* __restrict__ xq,
                                                                     float* __restrict__ scale) {
   __shared__ float sh[8];
+  // PDL: let the linear that consumes this output become resident and start its weight stream now; our own input may be
+  // the previous kernel's output, so wait for it before the first read
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * ldx);
   const int nv = K / 8;
   float amax = 0.f;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -175,29 +180,44 @@ __global__ void __launch_bounds__(256) fp8_fakequant_rowwise_kernel(const __nv_b
 
 using namespace ao;
 
-extern "C" int ao_fp8_fakequant_rowwise(const uint16_t* x, int M, int K, uint16_t* xq_bf16, float* scale,
-                                        void* stream) {
+extern "C" int ao_fp8_fakequant_rowwise_ld(const uint16_t* x, int ldx, int M, int K, uint16_t* xq_bf16, float* scale,
+                                           void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "fp8 fakequant: bad sizes M=%d K=%d", M, K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && xq_bf16 && scale, "fp8 fakequant: null pointer");
+  AO_REQUIRE(ldx >= K && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+             "fp8 fakequant: ldx=%d must be >= K=%d, a multiple of 8, x 16-byte aligned", ldx, K);
   AO_CUDA_CHECK(ao::launch(nvf4w::fp8_fakequant_rowwise_kernel, dim3(M), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), false, reinterpret_cast<const __nv_bfloat16*>(x), K,
+                           reinterpret_cast<cudaStream_t>(stream), pdl_enabled(), reinterpret_cast<const __nv_bfloat16*>(x), ldx, K,
                            reinterpret_cast<__nv_bfloat16*>(xq_bf16), scale));
   return AO_OK;
+}
+extern "C" int ao_fp8_fakequant_rowwise(const uint16_t* x, int M, int K, uint16_t* xq_bf16, float* scale, void* stream) {
+  return ao_fp8_fakequant_rowwise_ld(x, K, M, K, xq_bf16, scale, stream);
+}
+
+extern "C" int ao_nvfp4_weight_linear_ex(const uint16_t* x, int ldx, const float* x_scale, int M, int K, const uint8_t* wq,
+                                         const uint8_t* w_scale_blocked, const float* b_pts, int b_pts_per_row, int N,
+                                         const uint16_t* bias, uint16_t* y, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && N > 0, "nvfp4 weight linear: bad sizes M=%d K=%d N=%d", M, K, N);
+  AO_REQUIRE(K % 128 == 0, "nvfp4 weight linear: K=%d must be a multiple of 128", K);
+  AO_REQUIRE(N % 16 == 0, "nvfp4 weight linear: N=%d must be a multiple of 16 (inference_workflow.py:248-251)", N);
+  AO_REQUIRE(ldx >= K && ldx % 8 == 0, "nvfp4 weight linear: ldx=%d must be >= K=%d and a multiple of 8", ldx, K);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && wq && w_scale_blocked && y, "nvfp4 weight linear: null pointer");
+  AO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "nvfp4 weight linear: x must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 16) return nvf4w::launch_tc<16>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
+  if (M <= 32) return nvf4w::launch_tc<32>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
+  if (M <= 64) return nvf4w::launch_tc<64>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
+  return nvf4w::launch_tc<128>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
 }
 
 extern "C" int ao_nvfp4_weight_linear(const uint16_t* x, const float* x_scale, int M, int K, const uint8_t* wq,
                                       const uint8_t* w_scale_blocked, const float* b_pts, int N,
                                       const uint16_t* bias, uint16_t* y, void* workspace, size_t workspace_bytes,
                                       void* stream) {
-  AO_REQUIRE(M >= 0 && K > 0 && N > 0, "nvfp4 weight linear: bad sizes M=%d K=%d N=%d", M, K, N);
-  AO_REQUIRE(K % 128 == 0, "nvfp4 weight linear: K=%d must be a multiple of 128", K);
-  AO_REQUIRE(N % 16 == 0, "nvfp4 weight linear: N=%d must be a multiple of 16 (inference_workflow.py:248-251)", N);
-  if (M == 0) return AO_OK;
-  AO_REQUIRE(x && wq && w_scale_blocked && y, "nvfp4 weight linear: null pointer");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (M <= 16) return nvf4w::launch_tc<16>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
-  if (M <= 32) return nvf4w::launch_tc<32>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
-  if (M <= 64) return nvf4w::launch_tc<64>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
-  return nvf4w::launch_tc<128>(x, x_scale, M, K, wq, w_scale_blocked, b_pts, N, bias, y, workspace, workspace_bytes, st);
+  return ao_nvfp4_weight_linear_ex(x, K, x_scale, M, K, wq, w_scale_blocked, b_pts, 0, N, bias, y, workspace, workspace_bytes,
+                                   stream);
 }

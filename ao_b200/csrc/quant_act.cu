@@ -38,7 +38,7 @@ __device__ __forceinline__ float nanmax(float a, float b) {
 
 // ---------------------------------------------------------------- int8 / fp8 rowwise
 template <int MODE>  // 0 = int8, 1 = e4m3
-__global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                             int K, uint8_t* __restrict__ q,
                                                             float* __restrict__ scale) {
   __shared__ float sh[8];
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * ldx);   // row pitch ldx >= K (a column slice)
   const int nv = K / 8;
   float amax = 0.f;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -117,17 +117,25 @@ __device__ __forceinline__ float e8m0_recip(uint8_t e) {
 }
 
 // one thread per 32-element block
-__global__ void mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
+__global__ void mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
                                    uint8_t* __restrict__ q, uint8_t* __restrict__ sc, int swizzled) {
   // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
   // be the previous kernel's output, so wait for it before the first read
   pdl_launch_dependents();
   pdl_wait();
+  // one thread per 32-element block of the PADDED scale grid (rows to a multiple of 128, blocks to a multiple of 4 when
+  // the scales are written in the blocked layout): the padding entries are written as zero here, so no separate
+  // memset launch is needed (the GEMM multiplies them with TMA's zero fill: they must not be NaN)
   const int nb = K / 32;
+  const int nbp = swizzled ? ((nb + 3) & ~3) : nb, Mp = swizzled ? ((M + 127) & ~127) : M;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * nb) return;
-  const int m = idx / nb, kb = idx % nb;
-  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * K + kb * 32);
+  if (idx >= (size_t)Mp * nbp) return;
+  const int m = idx / nbp, kb = idx % nbp;
+  if (m >= M || kb >= nb) {
+    sc[blocked_index(m, kb, nbp / 4)] = 0;
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 32);
   uint4 v[4];
   float f[32];
   float amax = 0.f;
@@ -173,18 +181,23 @@ __device__ __forceinline__ uint32_t f32_to_e2m1(float f) {
 }
 
 // one thread per 16-element block
-__global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, int K,
+__global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
                                    const float* __restrict__ pts, uint8_t* __restrict__ q,
                                    uint8_t* __restrict__ sc, int swizzled) {
   // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
   // be the previous kernel's output, so wait for it before the first read
   pdl_launch_dependents();
   pdl_wait();
-  const int nb = K / 16;
+  const int nb = K / 16;   // padded scale grid as in mxfp8_quant_kernel
+  const int nbp = swizzled ? ((nb + 3) & ~3) : nb, Mp = swizzled ? ((M + 127) & ~127) : M;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * nb) return;
-  const int m = idx / nb, kb = idx % nb;
-  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * K + kb * 16);
+  if (idx >= (size_t)Mp * nbp) return;
+  const int m = idx / nbp, kb = idx % nbp;
+  if (m >= M || kb >= nb) {
+    sc[blocked_index(m, kb, nbp / 4)] = 0;
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 16);
   float f[16];
   float amax = 0.f;
 #pragma unroll
@@ -227,69 +240,75 @@ __global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int M, i
   *reinterpret_cast<uint2*>(q + (size_t)m * (K / 2) + kb * 8) = *reinterpret_cast<const uint2*>(o);
 }
 
-__global__ void zero_bytes_kernel(uint8_t* p, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0;
-}
-
 }  // namespace ao
 
 using namespace ao;
 
-extern "C" int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t* q, float* scale,
-                                        void* stream) {
+static int check_ld(const char* what, const void* x, int ldx, int K) {
+  AO_REQUIRE(ldx >= K && ldx % 8 == 0, "%s: ldx=%d must be >= K=%d and a multiple of 8", what, ldx, K);
+  AO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "%s: x must be 16-byte aligned", what);
+  return AO_OK;
+}
+
+extern "C" int ao_int8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, int K, int8_t* q, float* scale, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "int8 quantize: bad sizes M=%d K=%d (K%%8==0)", M, K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "int8 quantize: null pointer");
+  if (int rc = check_ld("int8 quantize", x, ldx, K)) return rc;
   AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<0>, dim3(M), dim3(256), 0,
                            reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), K, reinterpret_cast<uint8_t*>(q), scale));
+                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, K, reinterpret_cast<uint8_t*>(q), scale));
   return AO_OK;
 }
+extern "C" int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t* q, float* scale, void* stream) {
+  return ao_int8_quantize_rowwise_ld(x, K, M, K, q, scale, stream);
+}
 
-extern "C" int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t* q, float* scale,
-                                       void* stream) {
+extern "C" int ao_fp8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, int K, uint8_t* q, float* scale, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0, "fp8 quantize: bad sizes M=%d K=%d (K%%8==0)", M, K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "fp8 quantize: null pointer");
+  if (int rc = check_ld("fp8 quantize", x, ldx, K)) return rc;
   AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<1>, dim3(M), dim3(256), 0,
                            reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), K, q, scale));
+                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, K, q, scale));
   return AO_OK;
 }
+extern "C" int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t* q, float* scale, void* stream) {
+  return ao_fp8_quantize_rowwise_ld(x, K, M, K, q, scale, stream);
+}
 
-extern "C" int ao_mxfp8_quantize(const uint16_t* x, int M, int K, uint8_t* q, uint8_t* scale_e8m0,
-                                 int swizzled, void* stream) {
+extern "C" int ao_mxfp8_quantize_ld(const uint16_t* x, int ldx, int M, int K, uint8_t* q, uint8_t* scale_e8m0, int swizzled,
+                                    void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && K % 32 == 0, "mxfp8 quantize: K=%d must be a multiple of 32 (mx_tensor.py:244-246)", K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale_e8m0, "mxfp8 quantize: null pointer");
+  if (int rc = check_ld("mxfp8 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nb = K / 32;
-  if (swizzled) {
-    const size_t bytes = (size_t)ceil_div(M, 128) * ceil_div(nb, 4) * 512;
-    if (M % 128 != 0 || nb % 4 != 0)
-      AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e8m0, bytes));
-  }
-  const size_t total = (size_t)M * nb;
+  const size_t total = swizzled ? (size_t)ceil_div(M, 128) * 128 * (size_t)ceil_div(nb, 4) * 4 : (size_t)M * nb;
   AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), M, K, q, scale_e8m0, swizzled));
+                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, q, scale_e8m0, swizzled));
   return AO_OK;
 }
+extern "C" int ao_mxfp8_quantize(const uint16_t* x, int M, int K, uint8_t* q, uint8_t* scale_e8m0, int swizzled, void* stream) {
+  return ao_mxfp8_quantize_ld(x, K, M, K, q, scale_e8m0, swizzled, stream);
+}
 
-extern "C" int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* per_tensor_scale,
-                                 uint8_t* q, uint8_t* scale_e4m3, int swizzled, void* stream) {
+extern "C" int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, const float* per_tensor_scale, uint8_t* q,
+                                    uint8_t* scale_e4m3, int swizzled, void* stream) {
   AO_REQUIRE(M >= 0 && K > 0 && K % 16 == 0, "nvfp4 quantize: K=%d must be a multiple of 16", K);
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale_e4m3, "nvfp4 quantize: null pointer");
+  if (int rc = check_ld("nvfp4 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nb = K / 16;
-  if (swizzled) {
-    const size_t bytes = (size_t)ceil_div(M, 128) * ceil_div(nb, 4) * 512;
-    if (M % 128 != 0 || nb % 4 != 0)
-      AO_CUDA_CHECK(ao::launch(zero_bytes_kernel, dim3((unsigned)((bytes + 255) / 256)), dim3(256), 0, st, false, scale_e4m3, bytes));
-  }
-  const size_t total = (size_t)M * nb;
+  const size_t total = swizzled ? (size_t)ceil_div(M, 128) * 128 * (size_t)ceil_div(nb, 4) * 4 : (size_t)M * nb;
   AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), M, K, per_tensor_scale, q, scale_e4m3, swizzled));
+                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, per_tensor_scale, q, scale_e4m3, swizzled));
   return AO_OK;
+}
+extern "C" int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* per_tensor_scale, uint8_t* q,
+                                 uint8_t* scale_e4m3, int swizzled, void* stream) {
+  return ao_nvfp4_quantize_ld(x, K, M, K, per_tensor_scale, q, scale_e4m3, swizzled, stream);
 }

@@ -16,8 +16,9 @@ shards with ``narrow`` + ``copy_``; reference slicing support: torchao/testing/u
   parameters, now VIEWS of the fused storage (``narrow`` + ``copy_`` loaders keep working and write through);
 * a member's ``forward(x)`` returns its slice of the fused output.  The first member called with a given input runs
   the fused linear; the others recognise the same input (same storage, shape, strides and version counter) and
-  reuse that result.  A member called alone with a different input still returns the right values (the fused linear
-  simply runs for it).
+  reuse that result -- each member at most once per result, so the next forward pass (or CUDA-graph capture) over the
+  same buffer runs again.  A member called alone, or with a different input, still returns the right values (the
+  fused linear simply runs for it).
 
 The returned slices are strided views ``[..., n_i]`` of the fused ``[..., sum n]`` output; this engine's linears take
 a row-strided input directly (the TMA descriptor carries the row pitch), so feeding a slice to the next linear costs
@@ -85,8 +86,19 @@ def cat_out_features(ws: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
     if cls in (MXTensor, NVFP4Tensor):
         if w0.is_swizzled_scales and any(w.shape[0] % 128 != 0 for w in ws):
             return None   # a blocked scale tile spans 128 rows
-        if cls is NVFP4Tensor and any(w.per_tensor_scale is not None or w.act_per_tensor_scale is not None for w in ws):
-            return None   # one fp32 scalar per weight: cannot be shared by the group
+        pts = None
+        if cls is NVFP4Tensor:
+            from ao_b200.prototype.mx_formats.nvfp4_tensor import QuantizeTensorToFloat8ActKwargs
+
+            has = [w.per_tensor_scale is not None for w in ws]
+            if any(w.act_per_tensor_scale is not None for w in ws) or (any(has) and not all(has)):
+                return None
+            if all(has):
+                # one fp32 scalar per member: the weight-only / fp8-activation kernel takes one scale per out-feature
+                # (each member's scalar repeated over its rows); the nvfp4 x nvfp4 kernel folds a single scalar only
+                if not (w0.act_quant_kwargs is None or isinstance(w0.act_quant_kwargs, QuantizeTensorToFloat8ActKwargs)):
+                    return None
+                pts = torch.cat([w.per_tensor_scale.reshape(-1).float().expand(int(w.shape[0])) for w in ws]).contiguous()
         qd = torch.cat([w.qdata for w in ws], 0).contiguous()
         # blocked layout: 512-byte tiles ordered [row block][column block] -> row blocks concatenate
         sc = torch.cat([w.scale.reshape(-1) if w0.is_swizzled_scales else w.scale for w in ws], 0).contiguous()
@@ -95,7 +107,7 @@ def cat_out_features(ws: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
         if cls is MXTensor:
             return cls(qd, sc, w0.elem_dtype, w0.block_size, w0.orig_dtype, w0.kernel_preference, w0.act_quant_kwargs,
                        w0.is_swizzled_scales)
-        return cls(qd, sc, w0.block_size, w0.orig_dtype, None, None, w0.is_swizzled_scales, w0.use_triton_kernel,
+        return cls(qd, sc, w0.block_size, w0.orig_dtype, pts, None, w0.is_swizzled_scales, w0.use_triton_kernel,
                    w0.act_quant_kwargs)
     return None
 
@@ -110,16 +122,22 @@ class _Group:
         self.offsets = [sum(splits[:i]) for i in range(len(splits))]
         self._key = None
         self._out = None
+        self._served = set()
 
     @staticmethod
     def _key_of(x: torch.Tensor):
         return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version)
 
-    def run(self, x: torch.Tensor) -> torch.Tensor:
+    def run(self, x: torch.Tensor, member: int) -> torch.Tensor:
+        """Fused output for ``x`` on behalf of ``member``.  A cached result serves each member at most ONCE: the same
+        buffer handed in again (next forward pass, next CUDA-graph capture, a replayed graph's static input -- its
+        contents change without the version counter moving) is a new input and runs the fused linear again."""
         key = self._key_of(x)
-        if self._key != key or self._out is None:
+        if self._key != key or self._out is None or member in self._served:
             self._out = F.linear(x, self.weight, self.bias)
             self._key = key
+            self._served = set()
+        self._served.add(member)
         return self._out
 
 
@@ -137,7 +155,7 @@ class FusedLinearMember(nn.Linear):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         g = self._group
-        y = g.run(x)
+        y = g.run(x, self._index)
         off = g.offsets[self._index]
         return y[..., off: off + g.splits[self._index]]
 

@@ -18,7 +18,7 @@ from ao_b200.quantization.quantize_.common.kernel_preference import KernelPrefer
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
 from torch.utils._python_dispatch import return_and_correct_aliasing
 
-from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults, rows_for_kernel
 
 from .utils import from_blocked, hp_data_dims_to_swizzled_scale_dims_mx, slice_qdata_and_scale
 
@@ -79,7 +79,9 @@ class MXTensor(TorchAOBaseTensor):
         assert data_hp.dtype == torch.bfloat16, f"MXTensor.to_mx: bf16 input only in this engine, got {data_hp.dtype}"
         assert data_hp.shape[-1] % block_size == 0, (
             f"the last dimension of shape {data_hp.shape} must be divisible by block_size {block_size}")
-        assert data_hp.is_contiguous(), "unsupported"
+        # contiguous like the reference requires (mx_tensor.py:247), or a 2-D column slice (rows with a pitch): the
+        # quantizer kernel takes the pitch, no copy
+        assert data_hp.is_contiguous() or rows_for_kernel(data_hp) is data_hp, "unsupported"
         if elem_dtype != torch.float8_e4m3fn or block_size != 32:
             raise NotImplementedError("only mxfp8 (e4m3, block 32) is implemented (north-star formats)")
         if scaling_mode != ScaleCalculationMode.RCEIL:
@@ -126,7 +128,7 @@ def _(func, types, args, kwargs):
     x2 = x.reshape(-1, K)
     if x2.shape[0] == 0:
         return x.new_empty(*orig_shape[:-1], N)
-    xq = MXTensor.to_mx(x2.to(torch.bfloat16).contiguous(), k.elem_dtype, k.block_size, k.scaling_mode,
+    xq = MXTensor.to_mx(rows_for_kernel(x2.to(torch.bfloat16)), k.elem_dtype, k.block_size, k.scaling_mode,
                         k.kernel_preference, None, True)
     y = torch.ops.ao_b200.mxfp8_linear(xq.qdata, xq.scale.view(torch.uint8), w.qdata, w.scale.view(torch.uint8), bias)
     return y.reshape(*orig_shape[:-1], N).to(x.dtype)

@@ -18,7 +18,7 @@ import torch
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
 from torch.utils._python_dispatch import return_and_correct_aliasing
 
-from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults, rows_for_kernel
 
 from .utils import from_blocked, slice_qdata_and_scale
 
@@ -59,7 +59,10 @@ class NVFP4Tensor(TorchAOBaseTensor):
                  is_swizzled_scales=False, use_triton_kernel=False, act_quant_kwargs=None):
         super().__init__()
         if per_tensor_scale is not None:
-            assert per_tensor_scale.dim() == 0, "only a scalar per_tensor_scale is supported (no per-expert scales)"
+            # a scalar, like the reference (nvfp4_tensor.py:69-79); or one value per out-feature [N], which only
+            # ao_b200.fusion produces: a fused q|k|v / gate|up group keeps every member's own per-tensor scale
+            assert per_tensor_scale.dim() == 0 or (per_tensor_scale.dim() == 1 and per_tensor_scale.shape[0] == qdata.shape[-2]), (
+                "per_tensor_scale must be a scalar (or one value per out-feature for a fused group)")
         self.qdata = qdata
         self.scale = scale
         self.block_size = block_size
@@ -81,7 +84,7 @@ class NVFP4Tensor(TorchAOBaseTensor):
         assert data_hp.dim() == 2, "2-D tensors only"
         assert data_hp.dtype == torch.bfloat16, f"NVFP4Tensor.to_nvfp4: bf16 input only in this engine, got {data_hp.dtype}"
         assert data_hp.shape[-1] % block_size == 0, "K dim must be divisible by block_size"
-        assert data_hp.is_contiguous(), "Only support contiguous data for now"
+        assert data_hp.is_contiguous() or rows_for_kernel(data_hp) is data_hp, "Only support contiguous data (or a 2-D column slice)"
         pts = per_tensor_scale.reshape(()) if per_tensor_scale is not None else None
         q, s = torch.ops.ao_b200.nvfp4_quantize(data_hp, pts.reshape(1) if pts is not None else None, is_swizzled_scales)
         s = s.view(torch.float8_e4m3fn)
@@ -100,7 +103,7 @@ class NVFP4Tensor(TorchAOBaseTensor):
             s = from_blocked(s.reshape(-1), rows, K // self.block_size)
         s = s.reshape(rows, K // self.block_size).contiguous().view(torch.float8_e4m3fn).to(torch.float32)
         if self.per_tensor_scale is not None:
-            s = s * self.per_tensor_scale
+            s = s * (self.per_tensor_scale.reshape(-1, 1) if self.per_tensor_scale.dim() == 1 else self.per_tensor_scale)
         return (v * s.repeat_interleave(self.block_size, dim=1)).to(out)
 
 
@@ -121,19 +124,22 @@ def _(func, types, args, kwargs):
     if x2.shape[0] == 0:
         return x.new_empty(*orig_shape[:-1], N)
     k = w.act_quant_kwargs
-    b_pts = w.per_tensor_scale.reshape(1) if w.per_tensor_scale is not None else None
+    b_pts = w.per_tensor_scale.reshape(-1) if w.per_tensor_scale is not None else None
     if k is None:
-        # weight-only: y = x_bf16 @ dequant(W)^T, weights dequantised inside the tcgen05 kernel
-        y = torch.ops.ao_b200.nvfp4_weight_linear(x2.to(torch.bfloat16).contiguous(), None, w.qdata,
-                                                  w.scale.view(torch.uint8), b_pts, bias)
+        # weight-only: y = x_bf16 @ dequant(W)^T, weights dequantised inside the tcgen05 kernel; a column slice of a
+        # wider buffer goes in as is (the TMA descriptor carries the row pitch)
+        xb = rows_for_kernel(x2.to(torch.bfloat16))
+        y = torch.ops.ao_b200.nvfp4_weight_linear(xb, None, w.qdata, w.scale.view(torch.uint8), b_pts, bias)
         return y.reshape(*orig_shape[:-1], N).to(x.dtype)
+    assert w.per_tensor_scale is None or w.per_tensor_scale.dim() == 0 or isinstance(k, QuantizeTensorToFloat8ActKwargs), (
+        "a per-out-feature weight scale (fused group) is only supported by the weight-only / fp8-activation kernels")
     if isinstance(k, QuantizeTensorToFloat8ActKwargs):
         # NVFP4 weight x e4m3 rowwise activation (BASELINE config 5; defined in SURVEY §0-5 as
         # dequant(W_nvfp4) @ dequant(X_fp8 PerRow)): both dequants are exact in bf16.
-        xq, xs = torch.ops.ao_b200.fp8_fakequant_rowwise(x2.to(torch.bfloat16).contiguous())
+        xq, xs = torch.ops.ao_b200.fp8_fakequant_rowwise(rows_for_kernel(x2.to(torch.bfloat16)))
         y = torch.ops.ao_b200.nvfp4_weight_linear(xq, xs.reshape(-1), w.qdata, w.scale.view(torch.uint8), b_pts, bias)
         return y.reshape(*orig_shape[:-1], N).to(x.dtype)
-    xb = x2.to(torch.bfloat16).contiguous()
+    xb = rows_for_kernel(x2.to(torch.bfloat16))
     if k.use_dynamic_per_tensor_scale:
         a_pts = per_tensor_amax_to_scale(torch.max(torch.abs(xb))).reshape(1)
     else:
@@ -157,7 +163,10 @@ def _(func, types, args, kwargs):
     if step != 1:
         raise ValueError("Only support aten.slice with step=1")
     qd, sc = slice_qdata_and_scale(self, dim, start, end)
-    return return_and_correct_aliasing(func, args, kwargs, NVFP4Tensor(qd, sc, self.block_size, self.orig_dtype, self.per_tensor_scale, self.act_per_tensor_scale, self.is_swizzled_scales, self.use_triton_kernel, self.act_quant_kwargs))
+    pts = self.per_tensor_scale
+    if pts is not None and pts.dim() == 1 and dim == 0:
+        pts = aten.slice.Tensor(pts, 0, start, end, 1)   # per-out-feature scale of a fused group: follows the rows
+    return return_and_correct_aliasing(func, args, kwargs, NVFP4Tensor(qd, sc, self.block_size, self.orig_dtype, pts, self.act_per_tensor_scale, self.is_swizzled_scales, self.use_triton_kernel, self.act_quant_kwargs))
 
 
 @implements(aten.select.int)

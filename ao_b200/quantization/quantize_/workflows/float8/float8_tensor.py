@@ -20,7 +20,7 @@ from ao_b200.quantization.quant_primitives import (
 from ao_b200.quantization.quantize_.common.kernel_preference import KernelPreference
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
 from ao_b200.quantization.utils import get_block_size
-from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults, rows_for_kernel
 
 __all__ = ["Float8Tensor", "QuantizeTensorToFloat8Kwargs"]
 aten = torch.ops.aten
@@ -75,7 +75,7 @@ class Float8Tensor(TorchAOBaseTensor):
                 and hp_value_lb is None and hp_value_ub is None and hp_tensor.shape[-1] % 8 == 0
                 and kernel_preference in (KernelPreference.AUTO, KernelPreference.B200))
         if fast:
-            x2 = hp_tensor.reshape(-1, hp_tensor.shape[-1]).contiguous()
+            x2 = rows_for_kernel(hp_tensor.reshape(-1, hp_tensor.shape[-1]))
             data, scale = torch.ops.ao_b200.fp8_quantize_rowwise(x2)
             data = data.reshape(hp_tensor.shape)
             scale = scale.reshape(*hp_tensor.shape[:-1], 1)

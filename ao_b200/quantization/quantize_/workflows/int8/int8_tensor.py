@@ -18,7 +18,7 @@ from ao_b200.quantization.quant_primitives import (
     MappingType, choose_qparams_affine_int8, dequantize_affine_int8, quantize_affine_int8)
 from ao_b200.quantization.quantize_.common.quantize_tensor_kwargs import QuantizeTensorKwargs
 from ao_b200.quantization.utils import get_block_size
-from ao_b200.utils import TorchAOBaseTensor, fill_defaults
+from ao_b200.utils import TorchAOBaseTensor, fill_defaults, rows_for_kernel
 
 __all__ = ["Int8Tensor", "QuantizeTensorToInt8Kwargs"]
 aten = torch.ops.aten
@@ -76,7 +76,7 @@ class Int8Tensor(TorchAOBaseTensor):
                 and mapping_type == MappingType.SYMMETRIC and isinstance(granularity, PerRow)
                 and granularity.dim in (-1, hp_tensor.dim() - 1) and not reduce_range and hp_tensor.shape[-1] % 8 == 0)
         if fast:
-            x2 = hp_tensor.reshape(-1, hp_tensor.shape[-1]).contiguous()
+            x2 = rows_for_kernel(hp_tensor.reshape(-1, hp_tensor.shape[-1]))
             q, s = torch.ops.ao_b200.int8_quantize_rowwise(x2)
             int_data = q.reshape(hp_tensor.shape)
             scale = s.reshape(*hp_tensor.shape[:-1], 1)

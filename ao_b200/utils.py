@@ -18,9 +18,20 @@ from torch.utils._python_dispatch import return_and_correct_aliasing
 aten = torch.ops.aten
 
 __all__ = [
-    "TorchAOBaseTensor", "find_multiple", "fill_defaults", "is_sm_at_least_100", "is_sm_at_least_90",
+    "TorchAOBaseTensor", "find_multiple", "rows_for_kernel", "fill_defaults", "is_sm_at_least_100", "is_sm_at_least_90",
     "is_sm_at_least_89", "torch_version_at_least", "get_model_size_in_bytes",
 ]
+
+
+def rows_for_kernel(x2: torch.Tensor) -> torch.Tensor:
+    """2-D activations as this engine's kernels take them: unit inner stride, row pitch a multiple of 8 elements,
+    16-byte aligned start.  A column slice of a wider buffer (the q part of a fused q|k|v output) qualifies and is
+    passed through WITHOUT a copy -- the kernels get the pitch; anything else is made contiguous, which is what the
+    reference's handlers always do.  (Alignment is judged from the storage offset, not data_ptr(): handlers must
+    stay traceable with fake tensors.)"""
+    if x2.dim() == 2 and x2.stride(-1) == 1 and x2.stride(0) >= x2.shape[-1] and x2.stride(0) % 8 == 0 and x2.storage_offset() % 8 == 0:
+        return x2
+    return x2.contiguous()
 
 
 def find_multiple(n: int, k: int) -> int:

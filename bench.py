@@ -142,7 +142,7 @@ def algo_bytes(model_name, fmt, layers, bs):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def build_stack(model_name, config, layers, device, fuse=True, seed=0, init_scale=0.02):
+def build_stack(model_name, config, layers, device, fuse=True, seed=0):
     """Random-init Llama linear stack, quantized through the public API layer by layer (a 70B bf16 stack would not
     fit next to its quantized copy), then q|k|v and gate|up fused into one launch each."""
     import torch
@@ -154,13 +154,15 @@ def build_stack(model_name, config, layers, device, fuse=True, seed=0, init_scal
 
     h, i, kv, _ = SHAPES[model_name]
     shape = LlamaShape(model_name, h, i, kv, layers)
-    stack = LlamaLinearStack(shape, layers=0, device=device, seed=seed, init_scale=init_scale)
+    stack = LlamaLinearStack(shape, layers=0, device=device, seed=seed)
     gen = torch.Generator(device=device).manual_seed(seed)
     for _ in range(layers):
         layer = LlamaLinearLayer(shape, device)
         with torch.no_grad():
             for p in layer.parameters():
-                p.copy_((torch.randn(p.shape, device=device, generator=gen) * init_scale).to(p.dtype))
+                # unit gain per linear (std = 1 / sqrt(fan_in)): the 32- / 80-layer chain of bare linears neither
+                # overflows nor underflows bf16, so every GEMM of the step sees realistic magnitudes
+                p.copy_((torch.randn(p.shape, device=device, generator=gen) * (p.shape[-1] ** -0.5)).to(p.dtype))
         quantize_(layer, config)
         if fuse:
             fuse_parallel_linears(layer)

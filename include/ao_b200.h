@@ -160,11 +160,32 @@ int ao_nvfp4_weight_linear(const uint16_t* x, const float* x_scale, int M, int K
                            const uint8_t* wq, const uint8_t* w_scale_blocked,
                            const float* b_pts, int N, const uint16_t* bias, uint16_t* y,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Same with (a) a row-strided input (row m of x at x + m*ldx elements, ldx >= K, ldx % 8 == 0: e.g. a column slice
+ * of a fused projection's output) and (b) b_pts_per_row != 0: b_pts is one f32 scale PER OUTPUT FEATURE [N] instead of
+ * a scalar -- a fused q|k|v or gate|up group of NVFP4 weights keeps each member's own per-tensor scale
+ * (ao_b200/fusion.py; the reference has one scalar per NVFP4Tensor, nvfp4_tensor.py:69-79).                      */
+int ao_nvfp4_weight_linear_ex(const uint16_t* x, int ldx, const float* x_scale, int M, int K,
+                              const uint8_t* wq, const uint8_t* w_scale_blocked, const float* b_pts,
+                              int b_pts_per_row, int N, const uint16_t* bias, uint16_t* y,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* Per-token e4m3 quantisation that keeps the codes as bf16 values (exact): xq = bf16(e4m3(x/s)),
  * s = f32(bf16(amax/448)) -- the values Float8Tensor.from_hp(x, PerRow()) stores
  * (quant_primitives.py:2172-2287), in the operand type the bf16 MMA consumes. */
 int ao_fp8_fakequant_rowwise(const uint16_t* x, int M, int K, uint16_t* xq_bf16, float* scale,
                              void* stream);
+
+/* Row-strided variants of the activation quantizers: row m of x starts at x + m*ldx (elements; ldx >= K,
+ * ldx % 8 == 0, x 16-byte aligned) -- the input is a column slice of a wider buffer, e.g. the q part of a fused
+ * q|k|v projection's output.  The reference makes such inputs contiguous with a copy kernel first; here the pitch
+ * is a kernel argument.  Outputs are dense, exactly as in the functions without the suffix.                      */
+int ao_int8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, int K, int8_t* q, float* scale, void* stream);
+int ao_fp8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, int K, uint8_t* q, float* scale, void* stream);
+int ao_mxfp8_quantize_ld(const uint16_t* x, int ldx, int M, int K, uint8_t* q, uint8_t* scale_e8m0,
+                         int swizzled, void* stream);
+int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, const float* per_tensor_scale,
+                         uint8_t* q, uint8_t* scale_e4m3, int swizzled, void* stream);
+int ao_fp8_fakequant_rowwise_ld(const uint16_t* x, int ldx, int M, int K, uint16_t* xq_bf16, float* scale,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +33,7 @@ class Attn(nn.Module):
 
 def _configs():
     from ao_b200.prototype.mx_formats import MXDynamicActivationMXWeightConfig, NVFP4WeightOnlyConfig
+    from ao_b200.prototype.mx_formats.inference_workflow import NVFP4WeightFloat8ActivationConfig
     from ao_b200.quantization import (Float8DynamicActivationFloat8WeightConfig, Int4WeightOnlyConfig,
                                       Int8DynamicActivationInt8WeightConfig, PerRow)
 
@@ -40,11 +42,12 @@ def _configs():
         "int8": Int8DynamicActivationInt8WeightConfig(),
         "fp8": Float8DynamicActivationFloat8WeightConfig(granularity=PerRow()),
         "mxfp8": MXDynamicActivationMXWeightConfig(),
-        "nvfp4w": NVFP4WeightOnlyConfig(use_dynamic_per_tensor_scale=False),   # one fp32 scalar per weight cannot be shared
+        "nvfp4w": NVFP4WeightOnlyConfig(),   # two-level scaling: each member keeps its own per-tensor scale (per out-feature)
+        "nvfp4w_fp8a": NVFP4WeightFloat8ActivationConfig(),
     }
 
 
-@pytest.mark.parametrize("fmt", ["int4", "int8", "fp8", "mxfp8", "nvfp4w"])
+@pytest.mark.parametrize("fmt", ["int4", "int8", "fp8", "mxfp8", "nvfp4w", "nvfp4w_fp8a"])
 @pytest.mark.parametrize("M,bias", [(1, False), (32, True), (5, False)])
 def test_fused_matches_separate(fmt, M, bias):
     import ao_b200  # noqa: F401
@@ -74,6 +77,13 @@ def test_fused_matches_separate(fmt, M, bias):
             assert torch.equal(r, g)   # integer accumulation: exact whatever the split
         else:
             assert _sqnr(r, g) > 60.0
+    # the same buffer with NEW contents (a CUDA graph's static input): nothing stale may be served
+    x.copy_(torch.randn_like(x))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        again = m(x)
+        want = tuple(F.linear(x, getattr(m, n)._group.weight, getattr(m, n)._group.bias) for n in ("q_proj", "gate_proj"))
+    assert torch.equal(again[0], want[0][..., : again[0].shape[-1]]) and torch.equal(again[3], want[1][..., : again[3].shape[-1]])
     # a member called with a different input on its own still answers for that input
     x2 = torch.randn(M, 1024, device="cuda", dtype=torch.bfloat16)
     with torch.no_grad():
@@ -145,4 +155,35 @@ def test_llama_layer_chain_fused_vs_unfused():
             yb = b(x)
             n2 = torch.ops.ao_b200.launch_count()
         assert (n1 - n0, n2 - n1) == (14, 8)
+        with torch.no_grad():   # a second pass over the same buffer launches everything again (graph capture relies on it)
+            b(x)
+        assert torch.ops.ao_b200.launch_count() - n2 == 8
         assert _sqnr(ya, yb) > 40.0   # two layers of bf16 re-rounding between differently associated sums
+
+
+@pytest.mark.parametrize("M", [1, 5, 32, 130])
+def test_row_strided_quantizers_match_contiguous(M):
+    """The activation quantizers take a column slice of a wider buffer directly: same bytes as for its contiguous copy
+    (data, scales -- including the zero padding of the blocked scale layouts, which the kernels now write themselves)."""
+    import ao_b200  # noqa: F401
+
+    ops = torch.ops.ao_b200
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    K = 1056   # not a multiple of 128: the blocked scale layouts have padding columns
+    wide = torch.randn(M, K + 512, device="cuda", generator=gen).to(torch.bfloat16)
+    xs = wide[:, 256: 256 + K]
+    xc = xs.contiguous()
+    pts = torch.tensor([0.01], device="cuda")
+    for fn in (lambda t: ops.int8_quantize_rowwise(t), lambda t: ops.fp8_quantize_rowwise(t),
+               lambda t: ops.mxfp8_quantize(t, True), lambda t: ops.mxfp8_quantize(t, False),
+               lambda t: ops.nvfp4_quantize(t, pts, True), lambda t: ops.nvfp4_quantize(t, None, False),
+               lambda t: ops.fp8_fakequant_rowwise(t)):
+        a, b = fn(xs), fn(xc)
+        for u, v in zip(a, b):
+            assert torch.equal(u.view(torch.uint8) if u.element_size() == 1 else u, v.view(torch.uint8) if v.element_size() == 1 else v)
+    # padding entries of the blocked layouts are zero (they multiply TMA's zero fill in the GEMM: must not be NaN)
+    from oracle import oracle as o
+
+    _, s = ops.mxfp8_quantize(xs, True)
+    ref_q, ref_s = o.mxfp8_quantize(o.bf16_bits(xc))
+    assert np.array_equal(s.cpu().numpy().reshape(-1), o.to_blocked(ref_s).reshape(-1))
