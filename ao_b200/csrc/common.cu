@@ -124,6 +124,16 @@ int ts_min_units() {
   return v;
 }
 
+int ts_prefetch() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_TS_PREFETCH");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 4096) v = 0;
+  }
+  return v;
+}
+
 int ts_producers() {
   static int v = -1;
   if (v < 0) {

@@ -73,6 +73,7 @@ bool timeline_enabled();
 int ts_flags();  // AO_B200_TS_FLAGS bring-up switches for ts_gemm.cuh
 int ts_ctas_per_sm();  // AO_B200_TS_CTAS_PER_SM (1 or 2; default 0 = by problem size): grid of ts_gemm.cuh in CTAs per SM
 int ts_min_units();    // AO_B200_TS_MIN_UNITS (bring-up): minimum chunks per CTA of ts_gemm.cuh grids, 0 = by problem size
+int ts_prefetch();     // AO_B200_TS_PREFETCH (bring-up): L2 prefetch distance in chunks ahead of the ring's loads (default 0)
 int ts_producers();    // AO_B200_TS_PRODUCERS: weight TMA producer warps of ts_gemm.cuh (1 or 2; default 2)
 int sm_count();
 

@@ -54,6 +54,10 @@ struct Int4Fmt {
     uint4 v[4];
     uint32_t sz[4];
   };
+  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap* tm_sz, const tsg::Params& p, int n_tile, int kc) {
+    tma_prefetch_l2_3d(tm_w, 0, 4 * kc, n_tile * (ROWS / 8));
+    tma_prefetch_l2_2d(tm_sz, n_tile * ROWS, (kc * KCHUNK) / p.group_size);
+  }
   // thread r (= TMEM lane = weight row of the tile): 4 x ld.shared.v4 through the TMA 128-byte swizzle -- per
   // quarter-warp the eight rows hit eight different 16-byte bank groups: conflict-free (the half-row ld.shared.v2
   // of round 1 was 2-way conflicted: profiles/r01_int4_final_ncu_full.csv) -- and 4 x ld.shared.b32 of (s, z)

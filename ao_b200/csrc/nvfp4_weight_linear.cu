@@ -39,6 +39,10 @@ struct Nvfp4Fmt {
                  "l"(src), "r"(1024), "r"(smem_u32(bar))
                  : "memory");
   }
+  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p, int n_tile, int kc) {
+    tma_prefetch_l2_2d(tm_w, kc * 64, n_tile * ROWS);
+    bulk_prefetch_l2(p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512, 1024);
+  }
   // one weight row of the chunk: its 64 bytes (k 0..127, even k in the low nibble) and the 8 block scales
   struct Raw {
     uint4 v[4];

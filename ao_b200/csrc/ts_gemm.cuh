@@ -58,7 +58,7 @@ constexpr int WSTAGE_BYTES = W_BYTES + AUX_BYTES;  // one weight stage: packed n
 constexpr int NUM_THREADS = 16 * 32;
 
 // DBUF = accumulator buffers (2: the epilogue of a segment overlaps the next segment's MMAs)
-template <int N_MMA, int DBUF = 2>
+template <int N_MMA, int DBUF = 2, int XS = 0>
 struct Cfg {
   static constexpr int X_BYTES = 2 * N_MMA * 128;   // activation tile of one chunk (two 64-k swizzle atoms)
   static constexpr int TMEM_COLS = N_MMA <= 64 ? 256 : 512;
@@ -66,7 +66,7 @@ struct Cfg {
   static constexpr int A_COL0 = D_COLS <= 64 ? 64 : (D_COLS <= 128 ? 128 : 256);
   static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4 TMEM A stages
   // chunk slots = depth of the activation ring (see the header): 6 x 4 / 8 KB for the decode sizes
-  static constexpr int X_SLOTS = N_MMA <= 32 ? 6 : (N_MMA <= 64 ? 3 : 4);
+  static constexpr int X_SLOTS = N_MMA <= 32 ? (XS ? XS : 3) : (N_MMA <= 64 ? 3 : 4);
   static constexpr int BUDGET = N_MMA <= 64 ? 110 * 1024 : 172 * 1024;
   // weight stages (8, 6, 6 or 4).  A stage is consumed by whichever warpgroup its chunk belongs to; a consumer can
   // never be two phases away from the barrier it waits on (chunk i - STAGES was consumed before chunk i - 3 could
@@ -92,6 +92,7 @@ struct Params {
   int n_tiles, m_blocks, KT;   // KT = K/128
   int aux_col_blocks;
   int producers; // weight TMA producer warps (1 or 2)
+  int prefetch;  // bring-up: L2 prefetch distance in chunks (0 = off)
   int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs, 4 = no activation loads after the first ring-full
   unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
 };
@@ -464,6 +465,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           mbar_expect_tx(&wfull[s], Fmt::w_tx_bytes(p));
           Fmt::issue_w(&tm_w, &tm_aux, p, st, st + W_BYTES, &wfull[s], n_tile, kc, pol_w);
           fstamp(i, 0);
+          if (p.prefetch > 0 && i + p.prefetch < nunits) {   // HBM -> L2 of a chunk further down this CTA's range
+            const int u = u0 + i + p.prefetch;
+            Fmt::prefetch_w(&tm_w, &tm_aux, p, (u / p.KT) % p.n_tiles, u % p.KT);
+          }
         }
         __syncwarp();
         s += np;
@@ -516,7 +521,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         for (int j = 0; j < SX; ++j) {
           if (c < nunits) {
             mbar_wait(&cfull[j], cph);
-            tc_fence_after();
+            if (!(p.flags & 8)) tc_fence_after();   // bring-up: flag 8 drops the per-chunk tcgen05.fence of the issuer
             const uint32_t a_t = tmem_base + C::A_COL0 + (T_STATIC ? (j % T) : t_dyn) * A_COLS;
             if (elect_one()) {
               if (c == 0) stamp(4);
@@ -603,6 +608,7 @@ inline int plan(Params& p, void* ws, size_t ws_bytes, const char* what, int* gri
   p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + streamk::WS_PARTIAL_OFF);
   p.flags = ts_flags();
   p.producers = (ts_producers() == 1 || (Cfg<N_MMA>::STAGES & 1)) ? 1 : 2;
+  p.prefetch = ts_prefetch();
   *grid_out = grid;
   return AO_OK;
 }

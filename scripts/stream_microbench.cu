@@ -41,7 +41,7 @@ struct P {
   unsigned long long* sink;
 };
 
-__global__ void __launch_bounds__(512) stream_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_sz, const P p) {
+__global__ void __launch_bounds__(512) stream_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_sz, const __grid_constant__ CUtensorMap tm_w2, const P p) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * STAGE);
@@ -73,7 +73,15 @@ __global__ void __launch_bounds__(512) stream_kernel(const __grid_constant__ CUt
       if (i >= S) mbar_wait(&empty[s], ((i / S) & 1) ^ 1);
       const int tile = u / p.KT, kc = u % p.KT;
       uint8_t* st = smem + (size_t)s * STAGE;
-      if (p.mode == 0 || p.mode == 3) {
+      if (p.mode == 4) {
+        if (lane == 0) {   // weight box = 16 rows of 512 B (2-D, no swizzle) instead of 64 rows of 128 B
+          mbar_expect(&full[s], STAGE);
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(su32(st)),
+                       "l"(&tm_w2), "r"(su32(&full[s])), "r"(kc * 128), "r"(tile * 16), "l"(pol) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(su32(st + 8192)),
+                       "l"(&tm_sz), "r"(su32(&full[s])), "r"(tile * 128), "r"(kc * 4), "l"(pol) : "memory");
+        }
+      } else if (p.mode == 0 || p.mode == 3) {
         if (lane == 0) {
           mbar_expect(&full[s], STAGE);
           if (p.hint) {
@@ -150,14 +158,12 @@ int main(int argc, char** argv) {
   struct Cfg { int mode, S, prod, groups, hold, hint, backoff, hold_b; };
   // stages are a multiple of the consumer groups (a stage always belongs to the same group: parity waits cannot alias)
   const Cfg cfgs[] = {
-      {0, 9, 1, 3, 0, 1, 0, 0},     {0, 9, 2, 3, 0, 1, 0, 0},
-      {0, 9, 1, 3, 400, 1, 0, 600}, {0, 9, 2, 3, 400, 1, 0, 600}, {0, 6, 1, 3, 400, 1, 0, 600},  {0, 6, 2, 3, 400, 1, 0, 600},
-      {0, 9, 1, 3, 400, 1, 0, 1400}, {0, 9, 2, 3, 400, 1, 0, 1400}, {0, 9, 1, 3, 800, 1, 0, 1000}, {0, 9, 2, 3, 800, 1, 0, 1000},
-      {0, 9, 1, 3, 400, 1, 64, 600}, {0, 9, 2, 3, 400, 1, 64, 600}, {0, 18, 2, 3, 400, 1, 0, 600}, {0, 18, 2, 3, 800, 1, 0, 1000},
-      {3, 9, 1, 3, 400, 1, 0, 600}, {3, 9, 1, 3, 800, 1, 0, 1000}, {2, 9, 1, 3, 400, 0, 0, 600},  {2, 9, 2, 3, 400, 0, 0, 600},
+      {0, 6, 1, 3, 0, 1, 0, 0},     {4, 6, 1, 3, 0, 1, 0, 0},     {0, 6, 2, 3, 0, 1, 0, 0},     {4, 6, 2, 3, 0, 1, 0, 0},
+      {0, 6, 1, 3, 400, 1, 0, 600}, {4, 6, 1, 3, 400, 1, 0, 600}, {0, 6, 2, 3, 400, 1, 0, 600}, {4, 6, 2, 3, 400, 1, 0, 600},
+      {4, 12, 1, 3, 400, 1, 0, 600}, {4, 12, 2, 3, 0, 1, 0, 0},
   };
   for (const Cfg& c : cfgs) {
-    CUtensorMap tms[copies][2];
+    CUtensorMap tms[copies][3];
     for (int cc = 0; cc < copies; ++cc) {
       cuuint64_t d3[3] = {32, (cuuint64_t)4 * KT, (cuuint64_t)N / 8}, s3[2] = {128, (cuuint64_t)KT * 512};
       cuuint32_t b3[3] = {32, 4, 16}, e3[3] = {1, 1, 1};
@@ -168,12 +174,18 @@ int main(int argc, char** argv) {
       if (enc(&tms[cc][1], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sz + szbytes * cc, d2, s2, b2, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) { printf("enc sz failed\n"); return 1; }
     }
+    for (int cc = 0; cc < copies; ++cc) {
+      cuuint64_t d2[2] = {(cuuint64_t)KT * 128, (cuuint64_t)N / 8}, s2[1] = {(cuuint64_t)KT * 512};
+      cuuint32_t b2[2] = {128, 16}, e2[2] = {1, 1};
+      if (enc(&tms[cc][2], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, w + wbytes * cc, d2, s2, b2, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) { printf("enc w2 failed\n"); return 1; }
+    }
     const int grid = c.mode == 3 ? 2 * sms : sms;
     const size_t smem = (size_t)c.S * STAGE + 2 * MAXS * 8 + 1024 + 64;
     auto run = [&]() {
       for (int cc = 0; cc < copies; ++cc) {
         P p{w + wbytes * cc, sz + szbytes * cc, N, KT, n_tiles, c.S, c.mode, c.hold, c.prod, c.groups, c.hint, c.backoff, c.hold_b, sink};
-        stream_kernel<<<grid, 512, smem>>>(tms[cc][0], tms[cc][1], p);
+        stream_kernel<<<grid, 512, smem>>>(tms[cc][0], tms[cc][1], tms[cc][2], p);
       }
     };
     run();
