@@ -95,6 +95,107 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
   }
 }
 
+// ---------------------------------------------------------------- producer-fused rowwise quantizers
+// the activation quantization of a dynamic-activation linear fused with the op that produces the
+// activations, so the bf16 activations never travel to HBM and back:
+//   PRO 1  RMSNorm   y = bf16(w * bf16(x_f32 * rsqrt(mean(x_f32^2) + eps)))      (HF LlamaRMSNorm: fp32 statistics,
+//                                                                                  cast to the input dtype, * weight)
+//   PRO 2  SiLU-mul  y = bf16(bf16(silu_f32(g)) * u)                              (HF LlamaMLP: act_fn(gate) * up)
+// followed by exactly quant_rowwise_kernel's arithmetic on y (MODE 0 int8 per token, MODE 1 e4m3 per token).  One
+// CTA per token; the row of y is kept in shared memory between the abs-max pass and the cast pass.
+__device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = (l < nw) ? sh[l] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  return v;
+}
+
+template <int MODE, int PRO>
+__global__ void __launch_bounds__(256) fused_rowwise_kernel(const __nv_bfloat16* __restrict__ a, int lda,
+                                                            const __nv_bfloat16* __restrict__ b, int ldb, float eps,
+                                                            int K, uint8_t* __restrict__ q, float* __restrict__ scale) {
+  extern __shared__ uint4 yrow[];   // K / 8 vectors of 8 bf16
+  __shared__ float sh[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
+  const uint4* ar = reinterpret_cast<const uint4*>(a + (size_t)m * lda);
+  const uint4* br = reinterpret_cast<const uint4*>(PRO == 1 ? b : b + (size_t)m * ldb);   // weight[K] or up[m, :]
+  const int nv = K / 8;
+  float rstd = 0.f;
+  if (PRO == 1) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const uint4 v = ar[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+    ss = block_reduce_sum(ss, sh);
+    rstd = rsqrtf(ss / (float)K + eps);
+  }
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 va = ar[i], vb = br[i];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&va);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+    uint4 out;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]);
+      float y0, y1;
+      if (PRO == 1) {
+        y0 = bf16_round(fb.x * bf16_round(fa.x * rstd));
+        y1 = bf16_round(fb.y * bf16_round(fa.y * rstd));
+      } else {
+        y0 = bf16_round(bf16_round(fa.x / (1.f + expf(-fa.x))) * fb.x);
+        y1 = bf16_round(bf16_round(fa.y / (1.f + expf(-fa.y))) * fb.y);
+      }
+      ho[j] = __floats2bfloat162_rn(y0, y1);
+      amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
+    }
+    yrow[i] = out;
+  }
+  amax = block_reduce_max(amax, sh);   // (its __syncthreads also publish yrow)
+  float s;
+  if (MODE == 0) {
+    s = fmaxf(bf16_round(amax / 127.5f), 1.1920928955078125e-07f);
+  } else {
+    s = bf16_round(amax / 448.0f);
+  }
+  if (threadIdx.x == 0) scale[m] = s;
+  const float inv = 1.0f / s;
+  uint2* qr = reinterpret_cast<uint2*>(q + (size_t)m * K);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 v = yrow[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint8_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      if (MODE == 0) {
+        o[2 * j] = (uint8_t)(int8_t)(int)fminf(fmaxf(rintf(f.x * inv), -128.f), 127.f);
+        o[2 * j + 1] = (uint8_t)(int8_t)(int)fminf(fmaxf(rintf(f.y * inv), -128.f), 127.f);
+      } else {
+        float x0 = fminf(fmaxf(f.x / s, -448.f), 448.f), x1 = fminf(fmaxf(f.y / s, -448.f), 448.f);
+        if (s == 0.f) { x0 = __int_as_float(0x7fc00000); x1 = x0; }  // 0/0 = NaN in the reference
+        o[2 * j] = (uint8_t)__nv_cvt_float_to_fp8(x0, __NV_SATFINITE, __NV_E4M3);
+        o[2 * j + 1] = (uint8_t)__nv_cvt_float_to_fp8(x1, __NV_SATFINITE, __NV_E4M3);
+      }
+    }
+    qr[i] = *reinterpret_cast<const uint2*>(o);
+  }
+}
+
 // ---------------------------------------------------------------- block-scaled formats
 __device__ __forceinline__ size_t blocked_index(int r, int c, int col_blocks) {
   // mx_formats/utils.py:31-70: tile (r/128, c/4) of 512 bytes; (r%32)*16 + ((r%128)/32)*4 + c%4
@@ -244,6 +345,16 @@ __global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
 
 using namespace ao;
 
+template <int MODE, int PRO>
+static int launch_fused(const uint16_t* a, int lda, const uint16_t* b, int ldb, float eps, int M, int K, uint8_t* q, float* scale, void* stream) {
+  auto kern = fused_rowwise_kernel<MODE, PRO>;
+  const size_t smem = (size_t)K * 2;
+  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), 96 * 1024));
+  AO_CUDA_CHECK(ao::launch(kern, dim3(M), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
+                           reinterpret_cast<const __nv_bfloat16*>(a), lda, reinterpret_cast<const __nv_bfloat16*>(b), ldb, eps, K, q, scale));
+  return AO_OK;
+}
+
 static int check_ld(const char* what, const void* x, int ldx, int K) {
   AO_REQUIRE(ldx >= K && ldx % 8 == 0, "%s: ldx=%d must be >= K=%d and a multiple of 8", what, ldx, K);
   AO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "%s: x must be 16-byte aligned", what);
@@ -311,4 +422,31 @@ extern "C" int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, co
 extern "C" int ao_nvfp4_quantize(const uint16_t* x, int M, int K, const float* per_tensor_scale, uint8_t* q,
                                  uint8_t* scale_e4m3, int swizzled, void* stream) {
   return ao_nvfp4_quantize_ld(x, K, M, K, per_tensor_scale, q, scale_e4m3, swizzled, stream);
+}
+
+// RMSNorm -> per-token quantization.  x bf16 [M, K] with row pitch ldx, weight bf16 [K];
+// fmt 0 = int8 (scale = max(bf16(amax/127.5), eps32)), 1 = e4m3 (scale = bf16(amax/448)); q [M, K] bytes, scale f32 [M].
+extern "C" int ao_rmsnorm_quantize_rowwise(const uint16_t* x, int ldx, const uint16_t* weight, float eps, int M, int K, int fmt,
+                                           uint8_t* q, float* scale, void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0 && K <= 48 * 1024, "rmsnorm quantize: bad sizes M=%d K=%d (K%%8==0, K<=49152)", M, K);
+  AO_REQUIRE(fmt == 0 || fmt == 1, "rmsnorm quantize: fmt=%d (0 = int8, 1 = e4m3)", fmt);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(x && weight && q && scale, "rmsnorm quantize: null pointer");
+  if (int rc = check_ld("rmsnorm quantize", x, ldx, K)) return rc;
+  return fmt == 0 ? launch_fused<0, 1>(x, ldx, weight, 0, eps, M, K, q, scale, stream)
+                  : launch_fused<1, 1>(x, ldx, weight, 0, eps, M, K, q, scale, stream);
+}
+
+// SiLU(gate) * up -> per-token quantization.  gate / up bf16 [M, K] with row pitches ldg / ldu (the two halves of a
+// fused gate|up projection's output are column slices of one buffer).
+extern "C" int ao_silu_mul_quantize_rowwise(const uint16_t* gate, int ldg, const uint16_t* up, int ldu, int M, int K, int fmt,
+                                            uint8_t* q, float* scale, void* stream) {
+  AO_REQUIRE(M >= 0 && K > 0 && K % 8 == 0 && K <= 48 * 1024, "silu-mul quantize: bad sizes M=%d K=%d (K%%8==0, K<=49152)", M, K);
+  AO_REQUIRE(fmt == 0 || fmt == 1, "silu-mul quantize: fmt=%d (0 = int8, 1 = e4m3)", fmt);
+  if (M == 0) return AO_OK;
+  AO_REQUIRE(gate && up && q && scale, "silu-mul quantize: null pointer");
+  if (int rc = check_ld("silu-mul quantize", gate, ldg, K)) return rc;
+  if (int rc = check_ld("silu-mul quantize", up, ldu, K)) return rc;
+  return fmt == 0 ? launch_fused<0, 2>(gate, ldg, up, ldu, 0.f, M, K, q, scale, stream)
+                  : launch_fused<1, 2>(gate, ldg, up, ldu, 0.f, M, K, q, scale, stream);
 }

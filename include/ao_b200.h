@@ -187,6 +187,16 @@ int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, const float* 
 int ao_fp8_fakequant_rowwise_ld(const uint16_t* x, int ldx, int M, int K, uint16_t* xq_bf16, float* scale,
                                 void* stream);
 
+/* Producer-fused per-token quantizers ("fused with the preceding RMSNorm / SiLU where possible").
+ * They replace, for a dynamic-activation linear that follows an RMSNorm or a SiLU-gated product, the norm / activation
+ * kernel(s) + Int8Tensor.from_hp(x, PerRow()) / Float8Tensor.from_hp(x, PerRow()) (int8_tensor.py:176-248,
+ * float8_tensor.py:235-242) by one kernel; the quantization arithmetic is that of ao_int8/fp8_quantize_rowwise on the
+ * bf16 values the producer would have written (HF LlamaRMSNorm / LlamaMLP rounding points).  fmt: 0 int8, 1 e4m3.     */
+int ao_rmsnorm_quantize_rowwise(const uint16_t* x, int ldx, const uint16_t* weight, float eps, int M, int K,
+                                int fmt, uint8_t* q, float* scale, void* stream);
+int ao_silu_mul_quantize_rowwise(const uint16_t* gate, int ldg, const uint16_t* up, int ldu, int M, int K,
+                                 int fmt, uint8_t* q, float* scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

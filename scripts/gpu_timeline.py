@@ -60,6 +60,25 @@ for M in Ms:
                     continue
                 parts.append(f"{names[e]} {col.min():.1f}/{col.median():.1f}/{col.max():.1f}")
             print(f"   {nm:4s}" + "  ".join(parts))
+        # the slowest CTAs of the later kernel and where they sit in the stream-K split
+        KT, G = K // 128, 148
+        Ntiles = (N + 127) // 128
+        U = Ntiles * ((M + (16 if M <= 16 else 32 if M <= 32 else 64 if M <= 64 else 128) - 1) // (16 if M <= 16 else 32 if M <= 32 else 64 if M <= 64 else 128)) * KT
+        sl = slot(ws, 0) if ua[:, 0].min() >= ub[:, 0].min() else slot(ws, 1)
+        order = sorted(range(100), key=lambda i: -int(sl[i, 9]))[:6]
+        med = sorted(int(sl[i, 9]) for i in range(100) if int(sl[i, 9]) > 0)[50]
+        for bidx in order:
+            u0, u1 = U * bidx // G, U * (bidx + 1) // G
+            kc0, n = u0 % KT, u1 - u0
+            first = min(KT - kc0, n)
+            segs = [("contrib" if kc0 else ("full" if first == KT else "owner"), first)]
+            rest = n - first
+            while rest > 0:
+                c = min(KT, rest)
+                segs.append(("full" if c == KT else "owner", c))
+                rest -= c
+            row = "  ".join(f"{names[e]} {(int(sl[bidx, e]) - t0) / 1e3:.1f}" for e in (4, 5, 6, 8, 9) if int(sl[bidx, e]) > 0)
+            print(f"   slow CTA {bidx:3d} (+{(int(sl[bidx, 9]) - med) / 1e3:.1f} us vs median exit): units {n} segments {segs}: {row}")
         f = fine(ws, 0) if ua[:, 0].min() >= ub[:, 0].min() else fine(ws, 1)   # the later kernel's CTA 0
         if int(f[0, 0]) > 0:
             base = int(f[0, 0])
