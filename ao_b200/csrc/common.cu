@@ -95,6 +95,24 @@ bool timeline_enabled() {
   return v == 1;
 }
 
+bool prefill_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_NO_PREFILL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+bool prefetch_next_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_NO_PREFETCH_NEXT");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int ts_flags() {
   static int v = -1;
   if (v < 0) {

@@ -20,6 +20,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "ts_gemm.cuh"
+#include "ts_prefill.cuh"
 
 namespace ao {
 namespace int4k {
@@ -153,18 +154,16 @@ __global__ void int4_linear_simple_kernel(const __nv_bfloat16* __restrict__ x,
 }
 
 
-template <int N_MMA, int DBUF = 2>
-static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
-                     const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes,
-                     cudaStream_t stream) {
-  using C = tsg::Cfg<N_MMA, DBUF>;
+// tensor maps of the packed weights ({32 words, 4 row-pairs, 16 n8-tiles} box, 128-byte swizzle), the (scale, zero)
+// pairs and the activations (box = 64 k x `x_rows` tokens)
+static int make_maps(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
+                     int x_rows, CUtensorMap* tm_w, CUtensorMap* tm_sz, CUtensorMap* tm_x) {
   const int KT = K / 128;
-  CUtensorMap tm_w, tm_sz, tm_x;
   {
     const uint64_t dims[3] = {32, (uint64_t)4 * KT, (uint64_t)N / 8};
     const uint64_t str[2] = {128, (uint64_t)KT * 512};
     const uint32_t box[3] = {32, 4, 16};
-    int rc = make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, qdata, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_tmap(tm_w, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, qdata, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   const int gpc = g <= 128 ? 128 / g : 1;
@@ -172,16 +171,27 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K / g};
     const uint64_t str[1] = {(uint64_t)N * 4};
     const uint32_t box[2] = {128, (uint32_t)gpc};
-    int rc = make_tmap(&tm_sz, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sz, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    int rc = make_tmap(tm_sz, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sz, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)ldx * 2};
-    const uint32_t box[2] = {64, (uint32_t)N_MMA};
-    int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint32_t box[2] = {64, (uint32_t)x_rows};
+    int rc = make_tmap(tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  return AO_OK;
+}
+
+template <int N_MMA, int DBUF = 2>
+static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
+                     const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes,
+                     const ao_linear_extras* ex, cudaStream_t stream) {
+  using C = tsg::Cfg<N_MMA, DBUF>;
+  const int KT = K / 128;
+  CUtensorMap tm_w, tm_sz, tm_x;
+  if (int rc = make_maps(x, ldx, M, K, qdata, sz, g, N, N_MMA, &tm_w, &tm_sz, &tm_x)) return rc;
   tsg::Params p{};
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
@@ -191,6 +201,14 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   p.KT = KT;
   int grid = 0;
   if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
+  if (ex && prefetch_next_enabled()) {
+    for (int i = 0; i < 2; ++i) {
+      if (ex->prefetch_ptr[i] && (reinterpret_cast<uintptr_t>(ex->prefetch_ptr[i]) & 15) == 0 && ex->prefetch_bytes[i] < ((size_t)1 << 32)) {
+        p.pf_ptr[i] = reinterpret_cast<const uint8_t*>(ex->prefetch_ptr[i]);
+        p.pf_bytes[i] = (unsigned int)(ex->prefetch_bytes[i] & ~(size_t)127);
+      }
+    }
+  }
   // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 16 stamps + 8 chunks x 8 fine stamps at workspace + 20 MiB
   static unsigned tl_launch = 0;
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + ((size_t)20 << 20) +
@@ -204,14 +222,35 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   return AO_OK;
 }
 
+// M > 128 tokens: the prefill-shaped kernel (ts_prefill.cuh), weights dequantised once per 256 tokens
+static int launch_prefill(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
+                          const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  CUtensorMap tm_w, tm_sz, tm_x;
+  if (int rc = make_maps(x, ldx, M, K, qdata, sz, g, N, tsp::N_TOK, &tm_w, &tm_sz, &tm_x)) return rc;
+  tsg::Params p{};
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.M = M; p.N = N; p.N_out = N_out; p.K = K; p.group_size = g;
+  p.n_tiles = ceil_div(N_out, ROWS);
+  p.m_blocks = ceil_div(M, tsp::N_TOK);
+  p.KT = K / 128;
+  int grid = 0;
+  if (int rc = tsp::plan(p, ws, ws_bytes, "int4 linear (prefill)", &grid)) return rc;
+  auto kern = tsp::ts_prefill_kernel<Int4Fmt>;
+  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), tsp::SMEM_BYTES));
+  AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsp::NUM_THREADS), tsp::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_sz,
+                       tm_x, p));
+  return AO_OK;
+}
+
 }  // namespace int4k
 }  // namespace ao
 
-extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
-                                                 const uint16_t* scale_and_zero, int group_size, int N,
-                                                 const uint16_t* bias, uint16_t* y, int N_out,
-                                                 void* workspace, size_t workspace_bytes, int impl,
-                                                 void* stream) {
+extern "C" int ao_int4_tilepacked_linear_ex(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
+                                            const uint16_t* scale_and_zero, int group_size, int N,
+                                            const uint16_t* bias, uint16_t* y, int N_out,
+                                            void* workspace, size_t workspace_bytes, int impl,
+                                            const ao_linear_extras* extras, void* stream) {
   using namespace ao;
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "int4 linear: bad sizes M=%d K=%d N=%d", M, K, N);
   AO_REQUIRE(K % 1024 == 0, "int4 linear: K=%d must be a multiple of 1024 (format pads K)", K);
@@ -236,15 +275,27 @@ extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int
   }
   if (M <= 16)
     return int4k::launch_tc<16>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, st);
+                                workspace_bytes, extras, st);
   if (M <= 32)
     return int4k::launch_tc<32>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, st);
+                                workspace_bytes, extras, st);
   if (M <= 64)
     return int4k::launch_tc<64>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, st);
-  return int4k::launch_tc<128>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+                                workspace_bytes, extras, st);
+  if (M <= 128 || prefill_disabled())
+    return int4k::launch_tc<128>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+                                 workspace_bytes, extras, st);
+  return int4k::launch_prefill(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                workspace_bytes, st);
+}
+
+extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
+                                                 const uint16_t* scale_and_zero, int group_size, int N,
+                                                 const uint16_t* bias, uint16_t* y, int N_out,
+                                                 void* workspace, size_t workspace_bytes, int impl,
+                                                 void* stream) {
+  return ao_int4_tilepacked_linear_ex(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
+                                      workspace_bytes, impl, nullptr, stream);
 }
 
 extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qdata,

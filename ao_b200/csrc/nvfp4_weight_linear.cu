@@ -18,6 +18,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "ts_gemm.cuh"
+#include "ts_prefill.cuh"
 
 namespace ao {
 namespace nvf4w {
@@ -89,11 +90,13 @@ struct Nvfp4Fmt {
   }
 };
 
+// N_MMA = tokens per tile of the decode kernel (16 .. 128), or 0 = the prefill-shaped kernel (ts_prefill.cuh, 256 tokens)
 template <int N_MMA>
 static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, int K, const uint8_t* wq, const uint8_t* w_sf,
                      const float* b_pts, int b_pts_per_row, int N, const uint16_t* bias, uint16_t* y, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
-  using C = tsg::Cfg<N_MMA>;
+  constexpr bool PREFILL = N_MMA == 0;
+  constexpr int TOK = PREFILL ? tsp::N_TOK : N_MMA;
   CUtensorMap tm_w, tm_x;
   {
     const uint64_t dims[2] = {(uint64_t)K / 2, (uint64_t)N};
@@ -105,7 +108,7 @@ static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, in
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)ldx * 2};
-    const uint32_t box[2] = {64, (uint32_t)N_MMA};
+    const uint32_t box[2] = {64, (uint32_t)TOK};
     int rc = make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -119,14 +122,22 @@ static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, in
   p.aux_col_blocks = ceil_div(K / 16, 4);
   p.M = M; p.N = N; p.N_out = N; p.K = K; p.group_size = 16;
   p.n_tiles = ceil_div(N, ROWS);
-  p.m_blocks = ceil_div(M, N_MMA);
+  p.m_blocks = ceil_div(M, TOK);
   p.KT = K / 128;
   int grid = 0;
-  if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "nvfp4 weight linear", &grid)) return rc;
-  p.timeline = nullptr;
-  auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, N_MMA>;
-  AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
-  AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+  if constexpr (PREFILL) {
+    if (int rc = tsp::plan(p, ws, ws_bytes, "nvfp4 weight linear (prefill)", &grid)) return rc;
+    auto kern = tsp::ts_prefill_kernel<Nvfp4Fmt>;
+    AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), tsp::SMEM_BYTES));
+    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsp::NUM_THREADS), tsp::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+  } else {
+    using C = tsg::Cfg<(PREFILL ? 128 : N_MMA)>;
+    if (int rc = tsg::plan<(PREFILL ? 128 : N_MMA)>(p, ws, ws_bytes, "nvfp4 weight linear", &grid)) return rc;
+    p.timeline = nullptr;
+    auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, (PREFILL ? 128 : N_MMA)>;
+    AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
+    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+  }
   return AO_OK;
 }
 
@@ -215,7 +226,9 @@ extern "C" int ao_nvfp4_weight_linear_ex(const uint16_t* x, int ldx, const float
   if (M <= 16) return nvf4w::launch_tc<16>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
   if (M <= 32) return nvf4w::launch_tc<32>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
   if (M <= 64) return nvf4w::launch_tc<64>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
-  return nvf4w::launch_tc<128>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
+  if (M <= 128 || prefill_disabled())
+    return nvf4w::launch_tc<128>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
+  return nvf4w::launch_tc<0>(x, ldx, x_scale, M, K, wq, w_scale_blocked, b_pts, b_pts_per_row, N, bias, y, workspace, workspace_bytes, st);
 }
 
 extern "C" int ao_nvfp4_weight_linear(const uint16_t* x, const float* x_scale, int M, int K, const uint8_t* wq,

@@ -10,6 +10,7 @@
 // Inputs are bf16 [M,K]; HBM-bound elementwise/reduction work: 16-byte vector loads, one
 // pass for the reduction and one for the cast (the row stays in L1/L2).
 #include <cuda_bf16.h>
+#include <cuda_fp4.h>
 #include <cuda_fp8.h>
 
 #include "common.h"
@@ -92,6 +93,96 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
       }
     }
     qr[i] = *reinterpret_cast<const uint2*>(o);
+  }
+}
+
+// Same arithmetic, the row held in REGISTERS between the abs-max pass and the cast pass (K <= 16384): `tpr` threads
+// per row (32 .. 256, whole warps), 256 / tpr rows per CTA, up to 8 x 16-byte loads per thread all in flight before the
+// first use, packed hardware converts (cvt.rn.satfinite.e4m3x2.f32 / cvt.rni.sat.s8.f32).  The 2-pass kernel above
+// stays for longer rows.
+__device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {
+  int ia, ib, ic, id;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ia) : "f"(a));   // round-to-nearest-even + clamp to [-128, 127]
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ib) : "f"(b));
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ic) : "f"(c));
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(id) : "f"(d));
+  return (uint32_t)(ia & 0xff) | ((uint32_t)(ib & 0xff) << 8) | ((uint32_t)(ic & 0xff) << 16) | ((uint32_t)id << 24);
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+template <int MODE>  // 0 = int8, 1 = e4m3
+__global__ void __launch_bounds__(256) quant_rowwise_reg_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
+                                                                int tpr, uint8_t* __restrict__ q,
+                                                                float* __restrict__ scale) {
+  constexpr int VPT = 8;
+  __shared__ float sh[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row_in_cta = threadIdx.x / tpr, t = threadIdx.x % tpr;
+  const int m = blockIdx.x * (256 / tpr) + row_in_cta;
+  const bool active = m < M;
+  const int nv = K / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)(active ? m : 0) * ldx);
+  uint4 v[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int i = t + j * tpr;
+    v[j] = (active && i < nv) ? xr[i] : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h[e]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (tpr > 32) {   // (uniform) the row spans tpr / 32 warps
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sh[w] = amax;
+    __syncthreads();
+    const int w0 = row_in_cta * (tpr >> 5);
+    amax = sh[w0];
+    for (int i = 1; i < (tpr >> 5); ++i) amax = fmaxf(amax, sh[w0 + i]);
+  }
+  float s;
+  if (MODE == 0) s = fmaxf(bf16_round(amax / 127.5f), 1.1920928955078125e-07f);
+  else s = bf16_round(amax / 448.0f);
+  if (active && t == 0) scale[m] = s;
+  const float inv = 1.0f / s;
+  uint2* qr = reinterpret_cast<uint2*>(q + (size_t)(active ? m : 0) * K);
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int i = t + j * tpr;
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t2 = __bfloat1622float2(h[e]);
+      f[2 * e] = t2.x;
+      f[2 * e + 1] = t2.y;
+    }
+    uint2 o;
+    if (MODE == 0) {
+      o.x = pack_s8x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+      o.y = pack_s8x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] = fminf(fmaxf(f[e] / s, -448.f), 448.f);
+        if (s == 0.f) f[e] = __int_as_float(0x7fc00000);   // 0/0 = NaN in the reference
+      }
+      o.x = pack_e4m3x4(f[0], f[1], f[2], f[3]);
+      o.y = pack_e4m3x4(f[4], f[5], f[6], f[7]);
+    }
+    if (active && i < nv) qr[i] = o;
   }
 }
 
@@ -217,52 +308,71 @@ __device__ __forceinline__ float e8m0_recip(uint8_t e) {
   return __uint_as_float(bits);
 }
 
-// one thread per 32-element block
-__global__ void mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
-                                   uint8_t* __restrict__ q, uint8_t* __restrict__ sc, int swizzled) {
-  // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
-  // be the previous kernel's output, so wait for it before the first read
+// Zero entries of the PADDED blocked scale grid (rows to a multiple of 128, blocks to a multiple of 4): written by the
+// quantizer itself so no separate memset launch is needed (the GEMM multiplies them with TMA's zero fill: they must not
+// be NaN).  Called by every thread of the grid; the padding is (Mp - M) x nbp + M x (nbp - nb) entries.
+__device__ __forceinline__ void zero_scale_padding(uint8_t* sc, int M, int nb, size_t tid, size_t nthreads) {
+  const int nbp = (nb + 3) & ~3, Mp = (M + 127) & ~127;
+  const size_t pad_rows = (size_t)(Mp - M) * nbp, pad_cols = (size_t)M * (nbp - nb);
+  for (size_t i = tid; i < pad_rows + pad_cols; i += nthreads) {
+    int m, kb;
+    if (i < pad_rows) { m = M + (int)(i / nbp); kb = (int)(i % nbp); }
+    else { const size_t j = i - pad_rows; m = (int)(j / (nbp - nb)); kb = nb + (int)(j % (nbp - nb)); }
+    sc[blocked_index(m, kb, nbp / 4)] = 0;
+  }
+}
+
+// mxfp8: a 32-element block = FOUR lanes x 8 elements, so a warp reads 512 contiguous bytes per load instruction and
+// writes 256 (the one-thread-per-block layout of round 1 read 64 B per thread at a 64 B stride).  UNR vectors per
+// thread are loaded before the first is used.
+constexpr int BQ_UNR = 4, BQ_THREADS = 256;
+__global__ void __launch_bounds__(BQ_THREADS) mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
+                                                                 uint8_t* __restrict__ q, uint8_t* __restrict__ sc,
+                                                                 int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  // one thread per 32-element block of the PADDED scale grid (rows to a multiple of 128, blocks to a multiple of 4 when
-  // the scales are written in the blocked layout): the padding entries are written as zero here, so no separate
-  // memset launch is needed (the GEMM multiplies them with TMA's zero fill: they must not be NaN)
-  const int nb = K / 32;
-  const int nbp = swizzled ? ((nb + 3) & ~3) : nb, Mp = swizzled ? ((M + 127) & ~127) : M;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)Mp * nbp) return;
-  const int m = idx / nbp, kb = idx % nbp;
-  if (m >= M || kb >= nb) {
-    sc[blocked_index(m, kb, nbp / 4)] = 0;
-    return;
-  }
-  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 32);
-  uint4 v[4];
-  float f[32];
-  float amax = 0.f;
+  const int nvr = K / 8, nb = K / 32;   // vectors / blocks per row
+  const size_t total = (size_t)M * nvr;
+  const size_t base = (size_t)blockIdx.x * (BQ_THREADS * BQ_UNR) + threadIdx.x;
+  uint4 v[BQ_UNR];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[i] = src[i];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(h[j]);
-      f[i * 8 + 2 * j] = t.x;
-      f[i * 8 + 2 * j + 1] = t.y;
-      amax = nanmax(amax, nanmax(fabsf(t.x), fabsf(t.y)));
-    }
+  for (int u = 0; u < BQ_UNR; ++u) {
+    const size_t vi = base + (size_t)u * BQ_THREADS;
+    v[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (vi < total) v[u] = *reinterpret_cast<const uint4*>(x + (vi / nvr) * (size_t)ldx + (vi % nvr) * 8);
   }
   const float inv448 = (float)(1.0 / 448.0);
-  const uint8_t e = e8m0_rceil(amax * inv448);
-  const float r = e8m0_recip(e);
-  if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e;
-  else sc[(size_t)m * nb + kb] = e;
-  uint8_t o[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) o[i] = (uint8_t)__nv_cvt_float_to_fp8(f[i] * r, __NV_SATFINITE, __NV_E4M3);
-  uint4* dst = reinterpret_cast<uint4*>(q + (size_t)m * K + kb * 32);
-  dst[0] = reinterpret_cast<const uint4*>(o)[0];
-  dst[1] = reinterpret_cast<const uint4*>(o)[1];
+  for (int u = 0; u < BQ_UNR; ++u) {
+    const size_t vi = base + (size_t)u * BQ_THREADS;   // (K % 32 == 0: the four lanes of a block share `vi < total`)
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+    float f[8];
+    float amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h[e]);
+      f[2 * e] = t.x;
+      f[2 * e + 1] = t.y;
+      amax = nanmax(amax, nanmax(fabsf(t.x), fabsf(t.y)));
+    }
+    amax = nanmax(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = nanmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const uint8_t e8 = e8m0_rceil(amax * inv448);
+    const float r = e8m0_recip(e8);
+    if (vi < total) {
+      const int m = (int)(vi / nvr), cv = (int)(vi % nvr);
+      if ((cv & 3) == 0) {
+        const int kb = cv >> 2;
+        if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e8;
+        else sc[(size_t)m * nb + kb] = e8;
+      }
+      uint2 o;
+      o.x = pack_e4m3x4(f[0] * r, f[1] * r, f[2] * r, f[3] * r);
+      o.y = pack_e4m3x4(f[4] * r, f[5] * r, f[6] * r, f[7] * r);
+      *reinterpret_cast<uint2*>(q + (size_t)m * K + (size_t)cv * 8) = o;
+    }
+  }
+  if (swizzled) zero_scale_padding(sc, M, nb, (size_t)blockIdx.x * BQ_THREADS + threadIdx.x, (size_t)gridDim.x * BQ_THREADS);
 }
 
 // e2m1 RNE, saturating (custom_fp_utils.py:27-146): thresholds are the midpoints, ties to even
@@ -281,64 +391,73 @@ __device__ __forceinline__ uint32_t f32_to_e2m1(float f) {
   return s | c;
 }
 
-// one thread per 16-element block
-__global__ void nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
-                                   const float* __restrict__ pts, uint8_t* __restrict__ q,
-                                   uint8_t* __restrict__ sc, int swizzled) {
-  // PDL: let the linear that consumes this output become resident and prefetch its weights now; our own input may
-  // be the previous kernel's output, so wait for it before the first read
+// nvfp4: a 16-element block = TWO lanes x 8 elements (512 contiguous bytes read / 128 written per warp instruction);
+// e2m1 pairs by cvt.rn.satfinite.e2m1x2.f32 (RNE, saturating: the reference's rounding, custom_fp_utils.py:27-146),
+// NaN through the comparison chain above (the hardware convert canonicalises the sign).
+__device__ __forceinline__ uint32_t e2m1_pair(float a, float b) {
+  a = fminf(fmaxf(a, -6.f), 6.f);
+  b = fminf(fmaxf(b, -6.f), 6.f);
+  if (a != a || b != b) return f32_to_e2m1(a) | (f32_to_e2m1(b) << 4);
+  return (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(a, b), __NV_E2M1, cudaRoundNearest) & 0xffu;   // a in the LOW nibble
+}
+__global__ void __launch_bounds__(BQ_THREADS) nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
+                                                                 const float* __restrict__ pts, uint8_t* __restrict__ q,
+                                                                 uint8_t* __restrict__ sc, int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  const int nb = K / 16;   // padded scale grid as in mxfp8_quant_kernel
-  const int nbp = swizzled ? ((nb + 3) & ~3) : nb, Mp = swizzled ? ((M + 127) & ~127) : M;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)Mp * nbp) return;
-  const int m = idx / nbp, kb = idx % nbp;
-  if (m >= M || kb >= nb) {
-    sc[blocked_index(m, kb, nbp / 4)] = 0;
-    return;
+  const int nvr = K / 8, nb = K / 16;
+  const size_t total = (size_t)M * nvr;
+  const size_t base = (size_t)blockIdx.x * (BQ_THREADS * BQ_UNR) + threadIdx.x;
+  uint4 v[BQ_UNR];
+#pragma unroll
+  for (int u = 0; u < BQ_UNR; ++u) {
+    const size_t vi = base + (size_t)u * BQ_THREADS;
+    v[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (vi < total) v[u] = *reinterpret_cast<const uint4*>(x + (vi / nvr) * (size_t)ldx + (vi % nvr) * 8);
   }
-  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 16);
-  float f[16];
-  float amax = 0.f;
+  const float p = pts ? *pts : 1.f;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uint4 v = src[i];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  for (int u = 0; u < BQ_UNR; ++u) {
+    const size_t vi = base + (size_t)u * BQ_THREADS;   // (K % 16 == 0: the two lanes of a block share `vi < total`)
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+    float f[8];
+    float amax = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(h[j]);
-      f[i * 8 + 2 * j] = t.x;
-      f[i * 8 + 2 * j + 1] = t.y;
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h[e]);
+      f[2 * e] = t.x;
+      f[2 * e + 1] = t.y;
       amax = fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y)));
     }
-  }
-  const float bs = amax / 6.0f;
-  float recip;
-  uint8_t b8;
-  if (pts == nullptr) {
-    const float c = fminf(fmaxf(bs, 0.015625f), 448.f);
-    b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
-    const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
-    recip = 1.0f / bf;
-  } else {
-    const float p = *pts;
-    const float c = fminf(fmaxf(bs / p, 0.015625f), 448.f);
-    b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
-    const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
-    recip = (1.0f / p) / bf;
-  }
-  if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
-  else sc[(size_t)m * nb + kb] = b8;
-  uint8_t o[8];
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    const float bs = amax / 6.0f;
+    float recip;
+    uint8_t b8;
+    if (pts == nullptr) {
+      const float c = fminf(fmaxf(bs, 0.015625f), 448.f);
+      b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
+      const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
+      recip = 1.0f / bf;
+    } else {
+      const float c = fminf(fmaxf(bs / p, 0.015625f), 448.f);
+      b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
+      const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
+      recip = (1.0f / p) / bf;
+    }
+    if (vi < total) {
+      const int m = (int)(vi / nvr), cv = (int)(vi % nvr);
+      if ((cv & 1) == 0) {
+        const int kb = cv >> 1;
+        if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
+        else sc[(size_t)m * nb + kb] = b8;
+      }
+      uint32_t o = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float a = f[2 * i] * recip, b = f[2 * i + 1] * recip;
-    a = fminf(fmaxf(a, -6.f), 6.f);
-    b = fminf(fmaxf(b, -6.f), 6.f);
-    o[i] = (uint8_t)(f32_to_e2m1(a) | (f32_to_e2m1(b) << 4));  // even k in the LOW nibble
+      for (int e = 0; e < 4; ++e) o |= e2m1_pair(f[2 * e] * recip, f[2 * e + 1] * recip) << (8 * e);   // even k in the LOW nibble
+      *reinterpret_cast<uint32_t*>(q + (size_t)m * (K / 2) + (size_t)cv * 4) = o;
+    }
   }
-  *reinterpret_cast<uint2*>(q + (size_t)m * (K / 2) + kb * 8) = *reinterpret_cast<const uint2*>(o);
+  if (swizzled) zero_scale_padding(sc, M, nb, (size_t)blockIdx.x * BQ_THREADS + threadIdx.x, (size_t)gridDim.x * BQ_THREADS);
 }
 
 }  // namespace ao
@@ -355,6 +474,22 @@ static int launch_fused(const uint16_t* a, int lda, const uint16_t* b, int ldb, 
   return AO_OK;
 }
 
+template <int MODE>
+static int launch_rowwise(const uint16_t* x, int ldx, int M, int K, uint8_t* q, float* scale, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (K <= 16384) {
+    // threads per row: the fewest whole warps that hold the row in 8 vectors of 8 elements per thread
+    int tpr = 32;
+    while (tpr * 64 < K) tpr *= 2;
+    AO_CUDA_CHECK(ao::launch(quant_rowwise_reg_kernel<MODE>, dim3((unsigned)ceil_div(M, 256 / tpr)), dim3(256), 0, st,
+                             pdl_enabled(), xb, ldx, M, K, tpr, q, scale));
+  } else {
+    AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<MODE>, dim3(M), dim3(256), 0, st, pdl_enabled(), xb, ldx, K, q, scale));
+  }
+  return AO_OK;
+}
+
 static int check_ld(const char* what, const void* x, int ldx, int K) {
   AO_REQUIRE(ldx >= K && ldx % 8 == 0, "%s: ldx=%d must be >= K=%d and a multiple of 8", what, ldx, K);
   AO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "%s: x must be 16-byte aligned", what);
@@ -366,10 +501,7 @@ extern "C" int ao_int8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, in
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "int8 quantize: null pointer");
   if (int rc = check_ld("int8 quantize", x, ldx, K)) return rc;
-  AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<0>, dim3(M), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, K, reinterpret_cast<uint8_t*>(q), scale));
-  return AO_OK;
+  return launch_rowwise<0>(x, ldx, M, K, reinterpret_cast<uint8_t*>(q), scale, stream);
 }
 extern "C" int ao_int8_quantize_rowwise(const uint16_t* x, int M, int K, int8_t* q, float* scale, void* stream) {
   return ao_int8_quantize_rowwise_ld(x, K, M, K, q, scale, stream);
@@ -380,10 +512,7 @@ extern "C" int ao_fp8_quantize_rowwise_ld(const uint16_t* x, int ldx, int M, int
   if (M == 0) return AO_OK;
   AO_REQUIRE(x && q && scale, "fp8 quantize: null pointer");
   if (int rc = check_ld("fp8 quantize", x, ldx, K)) return rc;
-  AO_CUDA_CHECK(ao::launch(quant_rowwise_kernel<1>, dim3(M), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), pdl_enabled(),
-                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, K, q, scale));
-  return AO_OK;
+  return launch_rowwise<1>(x, ldx, M, K, q, scale, stream);
 }
 extern "C" int ao_fp8_quantize_rowwise(const uint16_t* x, int M, int K, uint8_t* q, float* scale, void* stream) {
   return ao_fp8_quantize_rowwise_ld(x, K, M, K, q, scale, stream);
@@ -396,9 +525,9 @@ extern "C" int ao_mxfp8_quantize_ld(const uint16_t* x, int ldx, int M, int K, ui
   AO_REQUIRE(x && q && scale_e8m0, "mxfp8 quantize: null pointer");
   if (int rc = check_ld("mxfp8 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nb = K / 32;
-  const size_t total = swizzled ? (size_t)ceil_div(M, 128) * 128 * (size_t)ceil_div(nb, 4) * 4 : (size_t)M * nb;
-  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
+  const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
+  const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
+  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, q, scale_e8m0, swizzled));
   return AO_OK;
 }
@@ -413,9 +542,9 @@ extern "C" int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, co
   AO_REQUIRE(x && q && scale_e4m3, "nvfp4 quantize: null pointer");
   if (int rc = check_ld("nvfp4 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nb = K / 16;
-  const size_t total = swizzled ? (size_t)ceil_div(M, 128) * 128 * (size_t)ceil_div(nb, 4) * 4 : (size_t)M * nb;
-  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, pdl_enabled(),
+  const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
+  const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
+  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, per_tensor_scale, q, scale_e4m3, swizzled));
   return AO_OK;
 }

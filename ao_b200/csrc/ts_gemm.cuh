@@ -95,7 +95,21 @@ struct Params {
   int prefetch;  // bring-up: L2 prefetch distance in chunks (0 = off)
   int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs, 4 = no activation loads after the first ring-full
   unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
+  // packed weights / scales of the linear that runs NEXT on this stream (ao_linear_extras): L2 prefetch hint
+  const uint8_t* pf_ptr[2];
+  unsigned int pf_bytes[2];      // multiples of 128
 };
+
+// This CTA's 1/G share of [base, base + bytes) as L2 prefetches, one piece per lane (whole warp calls).
+__device__ __forceinline__ void prefetch_share_l2(const uint8_t* base, unsigned int bytes, int b, int G, int lane) {
+  if (bytes == 0) return;
+  const unsigned int gran = bytes >> 7;   // 128-byte granules
+  const unsigned int g0 = (unsigned int)(((unsigned long long)gran * b) / G), g1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
+  const unsigned int per = (g1 - g0 + 31) / 32;
+  const unsigned int l0 = g0 + per * lane;
+  const unsigned int l1 = l0 + per < g1 ? l0 + per : g1;
+  if (l0 < l1) bulk_prefetch_l2(base + ((size_t)l0 << 7), (l1 - l0) << 7);
+}
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -357,6 +371,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     };
     // the segment whose last chunk is e belongs to warpgroup e % 3, which runs its epilogue after its next chunk
     int ep_seg = 0;
+    const bool eager0 = walk.seg_kind(0) == streamk::SEG_CONTRIB && nunits - walk.seg_count(0) < 12;
     auto seg_end = [&](int sg) { return walk.seg_begin(sg) + walk.seg_count(sg) - 1; };
     auto run_epilogues = [&](int before_chunk) {
       while (ep_seg < seg_last) {
@@ -425,7 +440,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (c >= SX) c -= SX;
       ec += DEQ_WGS;
       if (ec >= SX) { ec -= SX; eph ^= 1; }
-      run_epilogues(i);   // segments this warpgroup's EARLIER chunks completed: their accumulators are long done
+      // segments this warpgroup's EARLIER chunks completed: their accumulators are long done.  Exception: a short
+      // range's CONTRIB segment (always the first) is published as soon as its last chunk is stored -- its owner CTA
+      // is about to finish too and would otherwise wait for this flag (small projections: 6-10 chunks per CTA)
+      run_epilogues((eager0 && ep_seg == 0) ? i + 1 : i);
     }
     if (!waited_prev) { pdl_wait(); waited_prev = true; }
     run_epilogues(nunits);   // whatever is left of the segments before the last one
@@ -501,6 +519,11 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         if (++c == SX) { c = 0; cph ^= 1; }
         if (++kc == p.KT) { kc = 0; ++tile; }
       }
+      // Every TMA request of this CTA is out (the weight producers finished a ring depth earlier): HBM would now idle
+      // through this kernel's tail and the dependent-launch gap.  Issue this CTA's share of the NEXT linear's packed
+      // weights as L2 prefetches instead (hint from the launcher, ao_linear_extras).
+      prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+      prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);

@@ -1,5 +1,6 @@
 """Prefill-shaped runs (M >= 512) of the quantized linears: TFLOP/s against the measured bf16 tensor peak.
-  python scripts/gpu_prefill.py [int4|fp8|int8|mxfp8|nvfp4|all]"""
+  python scripts/gpu_prefill.py [int4|fp8|int8|all] [M,M,...] [NxK,NxK,...]
+AO_B200_NO_PREFILL=1 routes M > 128 through the decode kernel's 128-token blocks (the A/B baseline)."""
 import json
 import os
 import sys
@@ -31,15 +32,16 @@ def time_fn(fn, iters=5):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-def run(fmt):
-    shapes = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)]
-    for M in (512, 4096):
+def run(fmt, Ms, shapes):
+    for M in Ms:
         for (N, K) in shapes:
             x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+            lib = None
             if fmt == "int4":
                 qd = torch.randint(-2**31, 2**31 - 1, (N // 8, K // 128, 32, 4), device="cuda", dtype=torch.int32)
                 sz = ((torch.rand(K // 32, N, 2, device="cuda") - 0.5) * 0.004).to(torch.bfloat16)
                 fn = lambda: ops.int4_tilepacked_linear(x, qd, 32, sz, None, N, 1)
+                lib = lambda: torch.ops.aten._weight_int4pack_mm(x, qd, 32, sz)
                 mul = 1.0
             elif fmt in ("fp8", "int8"):
                 w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
@@ -56,10 +58,11 @@ def run(fmt):
                 mul = 2.0
             else:
                 continue
+            torch.cuda.synchronize()
             us = time_fn(fn)
             tf = 2.0 * M * N * K / us / 1e6
             extra = ""
-            if fmt in ("fp8", "int8"):
+            if lib is not None:
                 lus = time_fn(lib)
                 extra = f"  library {lus:8.1f} us ({2.0 * M * N * K / lus / 1e6:7.1f} TF)"
             xb = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -71,5 +74,8 @@ def run(fmt):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "int4"
+    Ms = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (512, 4096)
+    shapes = ([tuple(int(v) for v in s.split("x")) for s in sys.argv[3].split(",")] if len(sys.argv) > 3
+              else [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)])
     for f in (["int4", "fp8", "int8"] if which == "all" else [which]):
-        run(f)
+        run(f, Ms, shapes)

@@ -148,7 +148,8 @@ def test_nvfp4_linear(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,fp8_act", [(1, 256, 1024, False), (32, 4096, 4096, False), (7, 1024, 4096, True), (32, 8192, 8192, True),
-                                           (64, 1024, 2048, False), (130, 512, 1024, True)])
+                                           (64, 1024, 2048, False), (130, 512, 1024, True),
+                                           (512, 8192, 8192, True), (300, 1024, 4096, False)])  # M > 128: prefill kernel
 def test_nvfp4_weight_linear(ops, M, N, K, fp8_act):
     x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
