@@ -104,13 +104,23 @@ bool prefill_disabled() {
   return v == 1;
 }
 
-bool prefetch_next_enabled() {
+int prefetch_next_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AO_B200_NO_PREFETCH_NEXT");
-    v = (e && e[0] == '1') ? 0 : 1;
+    const char* e = getenv("AO_B200_PF_MODE");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 3) v = 1;
   }
-  return v == 1;
+  return v;
+}
+size_t prefetch_next_cap_bytes() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("AO_B200_PF_CAP_MB");
+    v = e ? atoll(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return (size_t)v << 20;
 }
 
 int ts_flags() {

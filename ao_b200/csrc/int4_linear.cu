@@ -201,11 +201,17 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   p.KT = KT;
   int grid = 0;
   if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
-  if (ex && prefetch_next_enabled()) {
+  if (ex && prefetch_next_mode() > 0) {
+    p.pf_mode = prefetch_next_mode();
+    const size_t cap = prefetch_next_cap_bytes();   // bring-up: total bytes per launch (0 = everything)
+    size_t total = 0;
+    for (int i = 0; i < 2; ++i) total += ex->prefetch_ptr[i] ? ex->prefetch_bytes[i] : 0;
     for (int i = 0; i < 2; ++i) {
       if (ex->prefetch_ptr[i] && (reinterpret_cast<uintptr_t>(ex->prefetch_ptr[i]) & 15) == 0 && ex->prefetch_bytes[i] < ((size_t)1 << 32)) {
+        size_t nbytes = ex->prefetch_bytes[i];
+        if (cap && total > cap) nbytes = (size_t)((double)nbytes * (double)cap / (double)total);
         p.pf_ptr[i] = reinterpret_cast<const uint8_t*>(ex->prefetch_ptr[i]);
-        p.pf_bytes[i] = (unsigned int)(ex->prefetch_bytes[i] & ~(size_t)127);
+        p.pf_bytes[i] = (unsigned int)(nbytes & ~(size_t)127);
       }
     }
   }

@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
 }
 
 template <int MODE>  // 0 = int8, 1 = e4m3
-__global__ void __launch_bounds__(256) quant_rowwise_reg_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
+__global__ void __launch_bounds__(256, 3) quant_rowwise_reg_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
                                                                 int tpr, uint8_t* __restrict__ q,
                                                                 float* __restrict__ scale) {
   constexpr int VPT = 8;
@@ -174,10 +174,22 @@ __global__ void __launch_bounds__(256) quant_rowwise_reg_kernel(const __nv_bfloa
       o.x = pack_s8x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
       o.y = pack_s8x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
     } else {
+      // x / s with the reference's IEEE rounding.  The row's scale is uniform, so its reciprocal is computed once and
+      // every quotient costs a multiply and ONE residual correction (q = x*r; q += (x - q*s) * r: what div.rn.f32
+      // itself does after refining the reciprocal; exact residual through the FMA).  Valid while nothing can leave the
+      // normal range: |x| <= amax ~ 448 s, so it is enough that s is far from 0 / inf; otherwise the plain division.
+      if (s >= 0x1p-64f && s <= 0x1p64f) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        f[e] = fminf(fmaxf(f[e] / s, -448.f), 448.f);
-        if (s == 0.f) f[e] = __int_as_float(0x7fc00000);   // 0/0 = NaN in the reference
+        for (int e = 0; e < 8; ++e) {
+          const float q0 = f[e] * inv;
+          f[e] = fminf(fmaxf(fmaf(fmaf(-q0, s, f[e]), inv, q0), -448.f), 448.f);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[e] = fminf(fmaxf(f[e] / s, -448.f), 448.f);
+          if (s == 0.f) f[e] = __int_as_float(0x7fc00000);   // 0/0 = NaN in the reference
+        }
       }
       o.x = pack_e4m3x4(f[0], f[1], f[2], f[3]);
       o.y = pack_e4m3x4(f[4], f[5], f[6], f[7]);
@@ -331,20 +343,31 @@ __global__ void __launch_bounds__(BQ_THREADS) mxfp8_quant_kernel(const __nv_bflo
                                                                  int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  const int nvr = K / 8, nb = K / 32;   // vectors / blocks per row
-  const size_t total = (size_t)M * nvr;
-  const size_t base = (size_t)blockIdx.x * (BQ_THREADS * BQ_UNR) + threadIdx.x;
+  const uint32_t nvr = K / 8, nb = K / 32;   // vectors / blocks per row
+  // vector u of this thread = linear index base + u * BQ_THREADS -> (row, vector in row), kept incrementally: one
+  // 32-bit division per thread (the launcher checks M * K / 8 < 2^32)
+  const uint32_t base = blockIdx.x * (uint32_t)(BQ_THREADS * BQ_UNR) + threadIdx.x;
+  uint32_t rm[BQ_UNR], rc[BQ_UNR];
+  {
+    uint32_t m = base / nvr, c = base - m * nvr;
+#pragma unroll
+    for (int u = 0; u < BQ_UNR; ++u) {
+      rm[u] = m;
+      rc[u] = c;
+      c += BQ_THREADS;
+      while (c >= nvr) { c -= nvr; ++m; }
+    }
+  }
   uint4 v[BQ_UNR];
 #pragma unroll
   for (int u = 0; u < BQ_UNR; ++u) {
-    const size_t vi = base + (size_t)u * BQ_THREADS;
     v[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (vi < total) v[u] = *reinterpret_cast<const uint4*>(x + (vi / nvr) * (size_t)ldx + (vi % nvr) * 8);
+    if (rm[u] < (uint32_t)M) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)rm[u] * ldx + rc[u] * 8);
   }
   const float inv448 = (float)(1.0 / 448.0);
 #pragma unroll
   for (int u = 0; u < BQ_UNR; ++u) {
-    const size_t vi = base + (size_t)u * BQ_THREADS;   // (K % 32 == 0: the four lanes of a block share `vi < total`)
+    const bool valid = rm[u] < (uint32_t)M;   // (K % 32 == 0: the four lanes of a block are in the same row)
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
     float f[8];
     float amax = 0.f;
@@ -359,8 +382,8 @@ __global__ void __launch_bounds__(BQ_THREADS) mxfp8_quant_kernel(const __nv_bflo
     amax = nanmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
     const uint8_t e8 = e8m0_rceil(amax * inv448);
     const float r = e8m0_recip(e8);
-    if (vi < total) {
-      const int m = (int)(vi / nvr), cv = (int)(vi % nvr);
+    if (valid) {
+      const int m = (int)rm[u], cv = (int)rc[u];
       if ((cv & 3) == 0) {
         const int kb = cv >> 2;
         if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e8;
@@ -405,20 +428,29 @@ __global__ void __launch_bounds__(BQ_THREADS) nvfp4_quant_kernel(const __nv_bflo
                                                                  uint8_t* __restrict__ sc, int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  const int nvr = K / 8, nb = K / 16;
-  const size_t total = (size_t)M * nvr;
-  const size_t base = (size_t)blockIdx.x * (BQ_THREADS * BQ_UNR) + threadIdx.x;
+  const uint32_t nvr = K / 8, nb = K / 16;
+  const uint32_t base = blockIdx.x * (uint32_t)(BQ_THREADS * BQ_UNR) + threadIdx.x;   // (see mxfp8_quant_kernel)
+  uint32_t rm[BQ_UNR], rc[BQ_UNR];
+  {
+    uint32_t m = base / nvr, c = base - m * nvr;
+#pragma unroll
+    for (int u = 0; u < BQ_UNR; ++u) {
+      rm[u] = m;
+      rc[u] = c;
+      c += BQ_THREADS;
+      while (c >= nvr) { c -= nvr; ++m; }
+    }
+  }
   uint4 v[BQ_UNR];
 #pragma unroll
   for (int u = 0; u < BQ_UNR; ++u) {
-    const size_t vi = base + (size_t)u * BQ_THREADS;
     v[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (vi < total) v[u] = *reinterpret_cast<const uint4*>(x + (vi / nvr) * (size_t)ldx + (vi % nvr) * 8);
+    if (rm[u] < (uint32_t)M) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)rm[u] * ldx + rc[u] * 8);
   }
   const float p = pts ? *pts : 1.f;
 #pragma unroll
   for (int u = 0; u < BQ_UNR; ++u) {
-    const size_t vi = base + (size_t)u * BQ_THREADS;   // (K % 16 == 0: the two lanes of a block share `vi < total`)
+    const bool valid = rm[u] < (uint32_t)M;   // (K % 16 == 0: the two lanes of a block are in the same row)
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
     float f[8];
     float amax = 0.f;
@@ -444,8 +476,8 @@ __global__ void __launch_bounds__(BQ_THREADS) nvfp4_quant_kernel(const __nv_bflo
       const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
       recip = (1.0f / p) / bf;
     }
-    if (vi < total) {
-      const int m = (int)(vi / nvr), cv = (int)(vi % nvr);
+    if (valid) {
+      const int m = (int)rm[u], cv = (int)rc[u];
       if ((cv & 1) == 0) {
         const int kb = cv >> 1;
         if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
@@ -526,6 +558,7 @@ extern "C" int ao_mxfp8_quantize_ld(const uint16_t* x, int ldx, int M, int K, ui
   if (int rc = check_ld("mxfp8 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
+  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS * BQ_UNR, "mxfp8 quantize: M*K too large (%d x %d)", M, K);
   const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
   AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, q, scale_e8m0, swizzled));
@@ -543,6 +576,7 @@ extern "C" int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, co
   if (int rc = check_ld("nvfp4 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
+  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS * BQ_UNR, "nvfp4 quantize: M*K too large (%d x %d)", M, K);
   const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
   AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, per_tensor_scale, q, scale_e4m3, swizzled));

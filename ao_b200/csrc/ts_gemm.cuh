@@ -67,12 +67,18 @@ struct Cfg {
   static constexpr int A_STAGES = (TMEM_COLS - A_COL0) / A_COLS;  // 3, 2 or 4 TMEM A stages
   // chunk slots = depth of the activation ring (see the header): 6 x 4 / 8 KB for the decode sizes
   static constexpr int X_SLOTS = N_MMA <= 32 ? (XS ? XS : 3) : (N_MMA <= 64 ? 3 : 4);
-  static constexpr int BUDGET = N_MMA <= 64 ? 110 * 1024 : 172 * 1024;
-  // weight stages (8, 6, 6 or 4).  A stage is consumed by whichever warpgroup its chunk belongs to; a consumer can
-  // never be two phases away from the barrier it waits on (chunk i - STAGES was consumed before chunk i - 3 could
-  // be stored, chunk i + STAGES cannot be issued before chunk i is consumed), so parity waits do not alias
+  static constexpr int BUDGET = N_MMA <= 64 ? 110 * 1024 : 190 * 1024;
+  // weight stages (8, 8, 6, 6).  A stage is consumed by whichever warpgroup its chunk belongs to, and a parity wait
+  // must never be TWO phases ahead of its barrier (waiting for chunk i + STAGES to land while chunk i has not landed
+  // yet returns at once: the stale phase has the same parity).  Two ways to rule that out:
+  //   * STAGES % 3 == 0: a stage always belongs to the same warpgroup, which takes its chunks in order;
+  //   * STAGES >= A_STAGES + 3: the warpgroup that wants chunk i + STAGES has stored chunk i + STAGES - 3 before,
+  //     which needed the MMAs of chunk i + STAGES - 3 - A_STAGES >= i, which needed chunk i dequantised.
+  // (Round 2 found the 128-token variant with 4 stages / 4 A stages violating both: sporadic wrong results and
+  // launch failures at 65..128 tokens; profiles/r02_call_k.log.)
   static constexpr int STAGES_RAW = (BUDGET - X_SLOTS * X_BYTES) / WSTAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW >= 6 ? (STAGES_RAW & ~1) : STAGES_RAW;   // even when there is room: two producers
+  static_assert(STAGES % 3 == 0 || STAGES >= A_STAGES + 3, "weight-stage parity waits could alias (see above)");
   static constexpr int X_OFF = STAGES * WSTAGE_BYTES;
   static constexpr int BAR_OFF = X_OFF + X_SLOTS * X_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)BAR_OFF + 1024 + 1024;
@@ -98,13 +104,19 @@ struct Params {
   // packed weights / scales of the linear that runs NEXT on this stream (ao_linear_extras): L2 prefetch hint
   const uint8_t* pf_ptr[2];
   unsigned int pf_bytes[2];      // multiples of 128
+  int pf_mode;                   // when to issue them: 1 = after the CTA's last TMA request, 2 = spread over its chunks,
+                                 // 3 = at kernel start (AO_B200_PF_MODE, bring-up)
 };
 
-// This CTA's 1/G share of [base, base + bytes) as L2 prefetches, one piece per lane (whole warp calls).
-__device__ __forceinline__ void prefetch_share_l2(const uint8_t* base, unsigned int bytes, int b, int G, int lane) {
+// Part `part` of `nparts` of this CTA's 1/G share of [base, base + bytes) as L2 prefetches, one piece per lane (whole
+// warp calls).
+__device__ __forceinline__ void prefetch_share_l2(const uint8_t* base, unsigned int bytes, int b, int G, int lane,
+                                                  int part = 0, int nparts = 1) {
   if (bytes == 0) return;
   const unsigned int gran = bytes >> 7;   // 128-byte granules
-  const unsigned int g0 = (unsigned int)(((unsigned long long)gran * b) / G), g1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
+  const unsigned int c0 = (unsigned int)(((unsigned long long)gran * b) / G), c1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
+  const unsigned int g0 = c0 + (unsigned int)(((unsigned long long)(c1 - c0) * part) / nparts);
+  const unsigned int g1 = c0 + (unsigned int)(((unsigned long long)(c1 - c0) * (part + 1)) / nparts);
   const unsigned int per = (g1 - g0 + 31) / 32;
   const unsigned int l0 = g0 + per * lane;
   const unsigned int l1 = l0 + per < g1 ? l0 + per : g1;
@@ -498,6 +510,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     } else if (warp == XTMA_WARP) {
       // ---------------------------------------------------------- activation producer
       const uint64_t pol_x = policy_evict_last();
+      if (p.pf_mode == 3) {
+        prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+        prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      }
       pdl_wait();   // activations are the previous kernel's output
       if (lane == 0) stamp(2);
       int c = 0, cph = 1, kc = kc_of(0), tile = tile_of(0);   // cph: parity of the slot's PREVIOUS use
@@ -516,14 +532,20 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           }
         }
         __syncwarp();
+        if (p.pf_mode == 2) {
+          prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane, i, nunits);
+          prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane, i, nunits);
+        }
         if (++c == SX) { c = 0; cph ^= 1; }
         if (++kc == p.KT) { kc = 0; ++tile; }
       }
       // Every TMA request of this CTA is out (the weight producers finished a ring depth earlier): HBM would now idle
       // through this kernel's tail and the dependent-launch gap.  Issue this CTA's share of the NEXT linear's packed
       // weights as L2 prefetches instead (hint from the launcher, ao_linear_extras).
-      prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-      prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      if (p.pf_mode == 1) {
+        prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+        prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      }
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(1 /*f32*/, 1 /*bf16*/, 1 /*bf16*/, ROWS, N_MMA);

@@ -12,7 +12,7 @@
 //     accumulator is single-buffered; a segment's epilogue is shared by the three dequant warpgroups (every third
 //     group of 8 token columns each) and DEFERRED by one chunk per warpgroup, so three chunks of the next segment are
 //     already dequantised when the accumulator is handed back and the MMAs restart at once
-//   * shared memory (1 CTA per SM): 4 weight stages (10 KB) + 5 activation slots of HALF a chunk (64 k x 256
+//   * shared memory (1 CTA per SM): 6 weight stages (10 KB) + 5 activation slots of HALF a chunk (64 k x 256
 //     tokens = 32 KB: what one TMA box / one 128-byte swizzle atom holds).  Activation slots have their own barrier
 //     pair (the decode kernel ties a chunk's activation tile to its A stage)
 //   * persistent stream-K with the owner-gather fix-up of streamk.cuh (tiles x K chunks split evenly over the
@@ -38,7 +38,8 @@ using tsg::W_BYTES;
 using tsg::WSTAGE_BYTES;
 
 constexpr int N_TOK = 256;                 // tokens per tile = UMMA N
-constexpr int S = 4;                       // weight stages
+constexpr int S = 6;                       // weight stages: a multiple of the 3 dequant warpgroups, so a stage always
+                                           // belongs to the same warpgroup and its parity waits cannot alias (ts_gemm.cuh)
 constexpr int T = 4;                       // TMEM A stages
 constexpr int XS = 5;                      // activation half-chunk slots
 constexpr int XH_BYTES = N_TOK * 128;      // 64 k x 256 tokens of bf16 = 32 KiB
@@ -49,6 +50,7 @@ constexpr int TMEM_COLS = 512, A_COL0 = 256;
 constexpr int DEQ_WGS = 3, DEQ_WARPS = 12, TMA_WARP = 12, MMA_WARP = 13, XTMA_WARP = 14;
 constexpr int NUM_THREADS = 16 * 32;
 static_assert(SMEM_BYTES <= 227 * 1024, "prefill kernel: shared memory budget");
+static_assert(S % DEQ_WGS == 0, "a weight stage must always belong to the same dequant warpgroup");
 
 __device__ __forceinline__ uint64_t policy_evict_normal() {
   uint64_t p;
@@ -200,7 +202,7 @@ ts_prefill_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     auto seg_end = [&](int sg) { return walk.seg_begin(sg) + walk.seg_count(sg) - 1; };
 
     for (int i = wg; i < nunits; i += DEQ_WGS) {
-      const int s = i & (S - 1), t = i & (T - 1);
+      const int s = i % S, t = i & (T - 1);
       const uint32_t st = smem_u32(smem + (size_t)s * WSTAGE_BYTES);
       const uint32_t a_t = lane_taddr + A_COL0 + t * A_COLS;
       mbar_wait(&wfull[s], (i / S) & 1);
@@ -233,7 +235,7 @@ ts_prefill_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     const uint64_t pol_w = policy_evict_normal();   // the same weight tile is read again for the next 256 tokens
     int kc = kc_of(0), n_tile = tile_of(0) % p.n_tiles;
     for (int i = 0; i < nunits; ++i) {
-      const int s = i & (S - 1);
+      const int s = i % S;
       if (i >= S) mbar_wait(&wempty[s], ((i / S) & 1) ^ 1);
       if (elect_one()) {
         uint8_t* st = smem + (size_t)s * WSTAGE_BYTES;

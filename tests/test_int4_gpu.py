@@ -157,6 +157,25 @@ def test_prefill_full_size_vs_aten_and_properties(ops, M, N, K):
     assert torch.equal(y2.float(), y.float() * 2)
 
 
+@pytest.mark.parametrize("M", [65, 100, 128, 512])
+def test_many_token_variants_are_stable_over_repeated_launches(ops, M):
+    """Regression (round 2): with 4 weight stages and 3 dequant warpgroups a warpgroup could pass the parity wait for
+    chunk i + 4 before chunk i had landed -- sporadic wrong results / launch failures of the 65..128-token variant (and of
+    the prefill kernel built on the same ring).  Short per-CTA ranges (a small projection) made it likely."""
+    N, K, g = 6144, 4096, 32
+    q, q_u8, sz = _mk_q(N, K, g, 5)
+    qd = ops.int4_pack_tile4d(q_u8, 8)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    ref = torch.ops.aten._weight_int4pack_mm(x, qd, g, sz)
+    y0 = ops.int4_tilepacked_linear(x, qd, g, sz, None, N, 1)
+    for _ in range(40):
+        y = ops.int4_tilepacked_linear(x, qd, g, sz, None, N, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y0)
+    d = (ref.float() - y.float()).norm()
+    assert d == 0 or 20 * torch.log10(ref.float().norm() / d) > 70.0
+
+
 def test_quantize_api_end_to_end(ops):
     """quantize_(Int4WeightOnlyConfig tile_packed_to_4d g=32): qparams/qdata bit-exact vs oracle, SQNR vs bf16 linear > 20 dB
     (the reference's own bar, test_int4_tile_packed_to_4d_tensor.py:54-69)."""

@@ -65,6 +65,26 @@ def test_activation_quantizers_bit_exact(ops, M, K):
         assert np.array_equal(o.bf16_to_f32(o.bf16_bits(qf)), o.e4m3_to_f32(qo)) and np.array_equal(sf.cpu().numpy().reshape(-1), so)
 
 
+@pytest.mark.parametrize("M,K", [(2048, 4096), (512, 16384), (300, 14336), (64, 32768)])
+def test_rowwise_quantizers_large_sample_vs_torch(ops, M, K):
+    """Millions of quotients per case against the reference arithmetic written with torch ops on the GPU (true IEEE
+    division, quant_primitives.py:2172-2287 / :1487-1583): the e4m3 kernel forms x / s as x * (1 / s) plus one FMA residual
+    correction, which must round exactly like the division; K = 32768 takes the two-pass kernel."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    x = (torch.randn(M, K, device="cuda", generator=g) * torch.logspace(-3, 3, M, device="cuda").unsqueeze(1)).to(torch.bfloat16)
+    q, s = ops.fp8_quantize_rowwise(x)
+    amax = x.abs().amax(dim=1, keepdim=True)
+    sc = (amax / 448.0).float()            # bf16 division, then f32 (the reference divides in the input dtype)
+    ref = (x.float() / sc).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    assert torch.equal(s.reshape(-1), sc.reshape(-1))
+    assert torch.equal(q.view(torch.uint8), ref.view(torch.uint8))
+    q8, s8 = ops.int8_quantize_rowwise(x)
+    sc8 = torch.clamp((amax / 127.5).float(), min=torch.finfo(torch.float32).eps)
+    ref8 = torch.clamp(torch.round(x.float() * (1.0 / sc8)), -128, 127).to(torch.int8)
+    assert torch.equal(s8.reshape(-1), sc8.reshape(-1))
+    assert torch.equal(q8, ref8)
+
+
 SHAPES = [(1, 128, 512), (16, 256, 1024), (32, 4096, 4096), (7, 1024, 4096), (32, 14336, 4096), (32, 4096, 14336),
           (64, 4096, 4096), (128, 1024, 2048), (200, 1024, 4096), (3, 144, 1024)]
 
