@@ -109,7 +109,7 @@ int prefetch_next_mode() {
   if (v < 0) {
     const char* e = getenv("AO_B200_PF_MODE");
     v = e ? atoi(e) : 1;
-    if (v < 0 || v > 3) v = 1;
+    if (v < 0 || v > 6) v = 1;
   }
   return v;
 }

@@ -334,66 +334,52 @@ __device__ __forceinline__ void zero_scale_padding(uint8_t* sc, int M, int nb, s
   }
 }
 
-// mxfp8: a 32-element block = FOUR lanes x 8 elements, so a warp reads 512 contiguous bytes per load instruction and
-// writes 256 (the one-thread-per-block layout of round 1 read 64 B per thread at a 64 B stride).  UNR vectors per
-// thread are loaded before the first is used.
-constexpr int BQ_UNR = 4, BQ_THREADS = 256;
+// mxfp8: one thread per 32-element block (64 contiguous bytes in, 32 out; a warp covers 2 KB of a row).  Measured
+// against a four-lanes-per-block variant with fully coalesced 16-byte accesses (profiles/r02_call_l.log: 3.9 TB/s):
+// the per-block work (abs-max, scale, reciprocal) is done once instead of four times and needs no shuffles, which
+// matters more than the access pattern -- the kernel is issue-bound, not sector-bound.  The NaN-propagating abs-max
+// runs on the bf16 BIT PATTERNS: |x| as an unsigned integer orders like the value and every NaN sorts above inf.
+constexpr int BQ_THREADS = 128;
 __global__ void __launch_bounds__(BQ_THREADS) mxfp8_quant_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
                                                                  uint8_t* __restrict__ q, uint8_t* __restrict__ sc,
                                                                  int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  const uint32_t nvr = K / 8, nb = K / 32;   // vectors / blocks per row
-  // vector u of this thread = linear index base + u * BQ_THREADS -> (row, vector in row), kept incrementally: one
-  // 32-bit division per thread (the launcher checks M * K / 8 < 2^32)
-  const uint32_t base = blockIdx.x * (uint32_t)(BQ_THREADS * BQ_UNR) + threadIdx.x;
-  uint32_t rm[BQ_UNR], rc[BQ_UNR];
-  {
-    uint32_t m = base / nvr, c = base - m * nvr;
+  const uint32_t nb = K / 32;
+  const uint32_t idx = blockIdx.x * BQ_THREADS + threadIdx.x;   // (the launcher checks M * nb < 2^32)
+  if (idx < (uint32_t)M * nb) {
+    const uint32_t m = idx / nb, kb = idx - m * nb;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 32);
+    uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < BQ_UNR; ++u) {
-      rm[u] = m;
-      rc[u] = c;
-      c += BQ_THREADS;
-      while (c >= nvr) { c -= nvr; ++m; }
+    for (int i = 0; i < 4; ++i) v[i] = src[i];
+    uint32_t mx = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mx = __vmaxu2(mx, v[i].x & 0x7FFF7FFFu);
+      mx = __vmaxu2(mx, v[i].y & 0x7FFF7FFFu);
+      mx = __vmaxu2(mx, v[i].z & 0x7FFF7FFFu);
+      mx = __vmaxu2(mx, v[i].w & 0x7FFF7FFFu);
     }
-  }
-  uint4 v[BQ_UNR];
-#pragma unroll
-  for (int u = 0; u < BQ_UNR; ++u) {
-    v[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (rm[u] < (uint32_t)M) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)rm[u] * ldx + rc[u] * 8);
-  }
-  const float inv448 = (float)(1.0 / 448.0);
-#pragma unroll
-  for (int u = 0; u < BQ_UNR; ++u) {
-    const bool valid = rm[u] < (uint32_t)M;   // (K % 32 == 0: the four lanes of a block are in the same row)
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
-    float f[8];
-    float amax = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __bfloat1622float2(h[e]);
-      f[2 * e] = t.x;
-      f[2 * e + 1] = t.y;
-      amax = nanmax(amax, nanmax(fabsf(t.x), fabsf(t.y)));
-    }
-    amax = nanmax(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-    amax = nanmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-    const uint8_t e8 = e8m0_rceil(amax * inv448);
+    const uint32_t abits = max(mx & 0xFFFFu, mx >> 16);
+    const float amax = __uint_as_float(abits << 16);          // NaN when any element was NaN
+    const uint8_t e8 = e8m0_rceil(amax * (float)(1.0 / 448.0));
     const float r = e8m0_recip(e8);
-    if (valid) {
-      const int m = (int)rm[u], cv = (int)rc[u];
-      if ((cv & 3) == 0) {
-        const int kb = cv >> 2;
-        if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e8;
-        else sc[(size_t)m * nb + kb] = e8;
-      }
-      uint2 o;
-      o.x = pack_e4m3x4(f[0] * r, f[1] * r, f[2] * r, f[3] * r);
-      o.y = pack_e4m3x4(f[4] * r, f[5] * r, f[6] * r, f[7] * r);
-      *reinterpret_cast<uint2*>(q + (size_t)m * K + (size_t)cv * 8) = o;
+    if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = e8;
+    else sc[(size_t)m * nb + kb] = e8;
+    uint4 o[2];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
+      const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+      const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+      ow[2 * i] = pack_e4m3x4(f0.x * r, f0.y * r, f1.x * r, f1.y * r);
+      ow[2 * i + 1] = pack_e4m3x4(f2.x * r, f2.y * r, f3.x * r, f3.y * r);
     }
+    uint4* dst = reinterpret_cast<uint4*>(q + (size_t)m * K + kb * 32);
+    dst[0] = o[0];
+    dst[1] = o[1];
   }
   if (swizzled) zero_scale_padding(sc, M, nb, (size_t)blockIdx.x * BQ_THREADS + threadIdx.x, (size_t)gridDim.x * BQ_THREADS);
 }
@@ -414,9 +400,9 @@ __device__ __forceinline__ uint32_t f32_to_e2m1(float f) {
   return s | c;
 }
 
-// nvfp4: a 16-element block = TWO lanes x 8 elements (512 contiguous bytes read / 128 written per warp instruction);
-// e2m1 pairs by cvt.rn.satfinite.e2m1x2.f32 (RNE, saturating: the reference's rounding, custom_fp_utils.py:27-146),
-// NaN through the comparison chain above (the hardware convert canonicalises the sign).
+// nvfp4: one thread per 16-element block (32 contiguous bytes in, 8 out); e2m1 pairs by cvt.rn.satfinite.e2m1x2.f32
+// (RNE, saturating: the reference's rounding, custom_fp_utils.py:27-146; round 1 used a seven-way comparison chain per
+// element), NaN through that chain (the hardware convert canonicalises the sign).
 __device__ __forceinline__ uint32_t e2m1_pair(float a, float b) {
   a = fminf(fmaxf(a, -6.f), 6.f);
   b = fminf(fmaxf(b, -6.f), 6.f);
@@ -428,40 +414,25 @@ __global__ void __launch_bounds__(BQ_THREADS) nvfp4_quant_kernel(const __nv_bflo
                                                                  uint8_t* __restrict__ sc, int swizzled) {
   pdl_launch_dependents();
   pdl_wait();
-  const uint32_t nvr = K / 8, nb = K / 16;
-  const uint32_t base = blockIdx.x * (uint32_t)(BQ_THREADS * BQ_UNR) + threadIdx.x;   // (see mxfp8_quant_kernel)
-  uint32_t rm[BQ_UNR], rc[BQ_UNR];
-  {
-    uint32_t m = base / nvr, c = base - m * nvr;
-#pragma unroll
-    for (int u = 0; u < BQ_UNR; ++u) {
-      rm[u] = m;
-      rc[u] = c;
-      c += BQ_THREADS;
-      while (c >= nvr) { c -= nvr; ++m; }
-    }
-  }
-  uint4 v[BQ_UNR];
-#pragma unroll
-  for (int u = 0; u < BQ_UNR; ++u) {
-    v[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (rm[u] < (uint32_t)M) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)rm[u] * ldx + rc[u] * 8);
-  }
-  const float p = pts ? *pts : 1.f;
-#pragma unroll
-  for (int u = 0; u < BQ_UNR; ++u) {
-    const bool valid = rm[u] < (uint32_t)M;   // (K % 16 == 0: the two lanes of a block are in the same row)
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
-    float f[8];
+  const uint32_t nb = K / 16;
+  const uint32_t idx = blockIdx.x * BQ_THREADS + threadIdx.x;   // (the launcher checks M * nb < 2^32)
+  if (idx < (uint32_t)M * nb) {
+    const uint32_t m = idx / nb, kb = idx - m * nb;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * ldx + kb * 16);
+    const uint4 v0 = src[0], v1 = src[1];
+    float f[16];
     float amax = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __bfloat1622float2(h[e]);
-      f[2 * e] = t.x;
-      f[2 * e + 1] = t.y;
-      amax = fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y)));
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(i == 0 ? &v0 : &v1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(h[j]);
+        f[i * 8 + 2 * j] = t.x;
+        f[i * 8 + 2 * j + 1] = t.y;
+        amax = fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y)));
+      }
     }
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
     const float bs = amax / 6.0f;
     float recip;
     uint8_t b8;
@@ -471,23 +442,22 @@ __global__ void __launch_bounds__(BQ_THREADS) nvfp4_quant_kernel(const __nv_bflo
       const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
       recip = 1.0f / bf;
     } else {
+      const float p = *pts;
       const float c = fminf(fmaxf(bs / p, 0.015625f), 448.f);
       b8 = (uint8_t)__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3);
       const float bf = __half2float(__half(__nv_cvt_fp8_to_halfraw(b8, __NV_E4M3)));
       recip = (1.0f / p) / bf;
     }
-    if (valid) {
-      const int m = (int)rm[u], cv = (int)rc[u];
-      if ((cv & 1) == 0) {
-        const int kb = cv >> 1;
-        if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
-        else sc[(size_t)m * nb + kb] = b8;
-      }
-      uint32_t o = 0;
+    if (swizzled) sc[blocked_index(m, kb, (nb + 3) / 4)] = b8;
+    else sc[(size_t)m * nb + kb] = b8;
+    uint2 o;
+    o.x = o.y = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o |= e2m1_pair(f[2 * e] * recip, f[2 * e + 1] * recip) << (8 * e);   // even k in the LOW nibble
-      *reinterpret_cast<uint32_t*>(q + (size_t)m * (K / 2) + (size_t)cv * 4) = o;
+    for (int e = 0; e < 4; ++e) {   // even k in the LOW nibble
+      o.x |= e2m1_pair(f[2 * e] * recip, f[2 * e + 1] * recip) << (8 * e);
+      o.y |= e2m1_pair(f[8 + 2 * e] * recip, f[8 + 2 * e + 1] * recip) << (8 * e);
     }
+    *reinterpret_cast<uint2*>(q + (size_t)m * (K / 2) + kb * 8) = o;
   }
   if (swizzled) zero_scale_padding(sc, M, nb, (size_t)blockIdx.x * BQ_THREADS + threadIdx.x, (size_t)gridDim.x * BQ_THREADS);
 }
@@ -557,10 +527,9 @@ extern "C" int ao_mxfp8_quantize_ld(const uint16_t* x, int ldx, int M, int K, ui
   AO_REQUIRE(x && q && scale_e8m0, "mxfp8 quantize: null pointer");
   if (int rc = check_ld("mxfp8 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
-  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS * BQ_UNR, "mxfp8 quantize: M*K too large (%d x %d)", M, K);
-  const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
-  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
+  const size_t total = (size_t)M * (K / 32);   // blocks = threads
+  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS, "mxfp8 quantize: M*K too large (%d x %d)", M, K);
+  AO_CUDA_CHECK(ao::launch(mxfp8_quant_kernel, dim3((unsigned)((total + BQ_THREADS - 1) / BQ_THREADS)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, q, scale_e8m0, swizzled));
   return AO_OK;
 }
@@ -575,10 +544,9 @@ extern "C" int ao_nvfp4_quantize_ld(const uint16_t* x, int ldx, int M, int K, co
   AO_REQUIRE(x && q && scale_e4m3, "nvfp4 quantize: null pointer");
   if (int rc = check_ld("nvfp4 quantize", x, ldx, K)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t total = (size_t)M * (K / 8);   // 16-byte vectors
-  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS * BQ_UNR, "nvfp4 quantize: M*K too large (%d x %d)", M, K);
-  const size_t per_cta = (size_t)BQ_THREADS * BQ_UNR;
-  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + per_cta - 1) / per_cta)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
+  const size_t total = (size_t)M * (K / 16);   // blocks = threads
+  AO_REQUIRE(total < ((size_t)1 << 32) - BQ_THREADS, "nvfp4 quantize: M*K too large (%d x %d)", M, K);
+  AO_CUDA_CHECK(ao::launch(nvfp4_quant_kernel, dim3((unsigned)((total + BQ_THREADS - 1) / BQ_THREADS)), dim3(BQ_THREADS), 0, st, pdl_enabled(),
                            reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, K, per_tensor_scale, q, scale_e4m3, swizzled));
   return AO_OK;
 }

@@ -104,8 +104,10 @@ struct Params {
   // packed weights / scales of the linear that runs NEXT on this stream (ao_linear_extras): L2 prefetch hint
   const uint8_t* pf_ptr[2];
   unsigned int pf_bytes[2];      // multiples of 128
-  int pf_mode;                   // when to issue them: 1 = after the CTA's last TMA request, 2 = spread over its chunks,
-                                 // 3 = at kernel start (AO_B200_PF_MODE, bring-up)
+  int pf_mode;                   // when / how to issue them (AO_B200_PF_MODE, bring-up): bulk prefetch 1 = after the CTA's
+                                 // last TMA request, 2 = spread over its chunks, 3 = at kernel start; per-line
+                                 // prefetch.global.L2 4 = after the last TMA request, 5 = at kernel start, 6 = after the
+                                 // weight producer's last request
 };
 
 // Part `part` of `nparts` of this CTA's 1/G share of [base, base + bytes) as L2 prefetches, one piece per lane (whole
@@ -121,6 +123,16 @@ __device__ __forceinline__ void prefetch_share_l2(const uint8_t* base, unsigned 
   const unsigned int l0 = g0 + per * lane;
   const unsigned int l1 = l0 + per < g1 ? l0 + per : g1;
   if (l0 < l1) bulk_prefetch_l2(base + ((size_t)l0 << 7), (l1 - l0) << 7);
+}
+// Same share, through the load/store unit instead of the TMA unit: one prefetch.global.L2 per 128-byte line, lanes on
+// consecutive lines.  (cp.async.bulk.prefetch.L2 turned out to be slow and to queue in front of the SM's later TMA
+// loads: profiles/r02_call_l.log, mode 2.)
+__device__ __forceinline__ void prefetch_share_l2_lsu(const uint8_t* base, unsigned int bytes, int b, int G, int lane) {
+  if (bytes == 0) return;
+  const unsigned int gran = bytes >> 7;
+  const unsigned int g0 = (unsigned int)(((unsigned long long)gran * b) / G), g1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
+  for (unsigned int g = g0 + lane; g < g1; g += 32)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)g << 7)) : "memory");
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -506,6 +518,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         kc += np;
         if (kc >= p.KT) { kc -= p.KT; if (++n_tile == p.n_tiles) n_tile = 0; }
       }
+      if (p.pf_mode == 6 && pi == 0) {   // (bring-up) LSU prefetch a ring depth earlier than mode 4
+        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      }
       pdl_wait();   // idle from here on: be ready to help with the last segment's outputs
     } else if (warp == XTMA_WARP) {
       // ---------------------------------------------------------- activation producer
@@ -513,6 +529,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (p.pf_mode == 3) {
         prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
         prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      }
+      if (p.pf_mode == 5) {
+        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
       }
       pdl_wait();   // activations are the previous kernel's output
       if (lane == 0) stamp(2);
@@ -545,6 +565,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (p.pf_mode == 1) {
         prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
         prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
+      }
+      if (p.pf_mode == 4) {
+        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
+        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
       }
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer

@@ -319,6 +319,14 @@ def run_ours(args):
         except Exception as ex:  # pragma: no cover
             sub = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
+    # ---- per-GEMM tensor-core roofline at prefill token counts (one GPU) ------------------------------------
+    prefill = None
+    if world == 1 and not args.quick:
+        try:
+            prefill = prefill_gemms(args, dev, peak_tf)
+        except Exception as ex:  # pragma: no cover
+            prefill = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +366,8 @@ def run_ours(args):
                 gpu_ref[key]["speedup"] = gpu_ref[key]["ms_per_step"] / ours_ms
     if sub is not None:
         out["configs"] = sub
+    if prefill is not None:
+        out["prefill"] = prefill
     if world == 1:
         out["cpu_baseline"] = cpu_baseline(args.bs)
     print(json.dumps(out))
@@ -426,6 +436,70 @@ def gpu_reference_int4(model, hidden, batch_sizes, args, dev, barrier):
         rec["value"] = bs / (best * 1e-3)
         rec["unit"] = "tok/s"
         out[f"bs{bs}"] = rec
+    return out
+
+
+def prefill_gemms(args, dev, peak_tf):
+    """Per-GEMM tensor-core roofline at prefill token counts (the only place the north star's
+    ">= 70 % of the tensor-core roofline" clause applies): the four fused Llama-3-8B projections at M = 512 and 4096,
+    int4 weight-only (the prefill-shaped TS kernel, csrc/ts_prefill.cuh) with the kernel the reference calls
+    (aten._weight_int4pack_mm, M = 512 only: it needs tens of milliseconds at 4096) and cuBLAS bf16 (F.linear on
+    bf16 weights, what `peak_tf` was measured with) beside it; fp8-rowwise and int8-dynamic with their library kernels.
+    TFLOP/s = 2 M N K / time, CUDA events over back-to-back launches on weights + activations larger than L2 for
+    the big shapes; `frac` is against the measured bf16 peak (x2 for the 8-bit kinds)."""
+    import torch
+
+    ops = torch.ops.ao_b200
+    h, inter, kv, _ = SHAPES["llama-3-8b"]
+    shapes = [("qkv", h + 2 * kv, h), ("o", h, h), ("gate_up", 2 * inter, h), ("down", h, inter)]
+
+    def t_us(fn, iters):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    out = {"peak_bf16_tflops": peak_tf, "unit": "TFLOP/s", "note": "one GEMM per entry; frac = TFLOP/s over the measured bf16 "
+           "tensor peak (x2 for fp8 / int8); int4 runs ao::tsp::ts_prefill_kernel, fp8 / int8 run lowp_linear_kernel in 128-token blocks"}
+    for M in (512, 4096):
+        for name, N, K in shapes:
+            flops = 2.0 * M * N * K
+            x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+            rec = {}
+            qd = torch.randint(-2**31, 2**31 - 1, (N // 8, K // 128, 32, 4), device=dev, dtype=torch.int32)
+            sz = ((torch.rand(K // GROUP, N, 2, device=dev) - 0.5) * 0.004).to(torch.bfloat16)
+            us = t_us(lambda: ops.int4_tilepacked_linear(x, qd, GROUP, sz, None, N, 1), 5)
+            rec["int4"] = {"us": us, "tflops": flops / us / 1e6, "frac": flops / us / 1e6 / peak_tf}
+            if M == 512:
+                lus = t_us(lambda: torch.ops.aten._weight_int4pack_mm(x, qd, GROUP, sz), 2)
+                rec["int4"]["aten_int4pack_mm_us"] = lus
+            del qd, sz
+            w = torch.randn(N, K, device=dev).to(torch.bfloat16)
+            rec["bf16_cublas_us"] = t_us(lambda: torch.nn.functional.linear(x, w), 5)
+            for fmt in ("fp8", "int8"):
+                if fmt == "fp8":
+                    wq, ws = ops.fp8_quantize_rowwise(w)
+                    xq, xs = ops.fp8_quantize_rowwise(x)
+                    fn = lambda: ops.fp8_rowwise_linear(xq, xs.reshape(-1), wq, ws.reshape(-1), None)
+                    lib = lambda: torch._scaled_mm(xq, wq.t(), scale_a=xs.reshape(-1, 1), scale_b=ws.reshape(1, -1),
+                                                   out_dtype=torch.bfloat16, use_fast_accum=True)
+                else:
+                    wq, ws = ops.int8_quantize_rowwise(w)
+                    xq, xs = ops.int8_quantize_rowwise(x)
+                    fn = lambda: ops.int8_dyn_linear(xq, xs.reshape(-1), wq, ws.reshape(-1), None)
+                    lib = lambda: torch._int_mm(xq, wq.t())
+                us = t_us(fn, 5)
+                rec[fmt] = {"us": us, "tflops": flops / us / 1e6, "frac": flops / us / 1e6 / (2 * peak_tf), "library_us": t_us(lib, 5)}
+                del wq, ws, xq, xs
+            out[f"M{M}_{name}"] = rec
+            del x, w
+            torch.cuda.empty_cache()
     return out
 
 
