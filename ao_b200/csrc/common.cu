@@ -104,25 +104,6 @@ bool prefill_disabled() {
   return v == 1;
 }
 
-int prefetch_next_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AO_B200_PF_MODE");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 6) v = 1;
-  }
-  return v;
-}
-size_t prefetch_next_cap_bytes() {
-  static long long v = -1;
-  if (v < 0) {
-    const char* e = getenv("AO_B200_PF_CAP_MB");
-    v = e ? atoll(e) : 0;
-    if (v < 0) v = 0;
-  }
-  return (size_t)v << 20;
-}
-
 int ts_flags() {
   static int v = -1;
   if (v < 0) {

@@ -72,10 +72,6 @@ bool pdl_enabled();
 bool timeline_enabled();
 // AO_B200_NO_PREFILL=1: M > 128 goes through the decode kernel's 128-token blocks instead of ts_prefill.cuh (A/B runs).
 bool prefill_disabled();
-// AO_B200_PF_MODE: when a CTA issues the next-weights L2 prefetch of ao_linear_extras (0 = never, 1 = after its last
-// TMA request, 2 = spread over its chunks, 3 = at kernel start); AO_B200_PF_CAP_MB: bytes per launch (0 = all).
-int prefetch_next_mode();
-size_t prefetch_next_cap_bytes();
 int ts_flags();  // AO_B200_TS_FLAGS bring-up switches for ts_gemm.cuh
 int ts_ctas_per_sm();  // AO_B200_TS_CTAS_PER_SM (1 or 2; default 0 = by problem size): grid of ts_gemm.cuh in CTAs per SM
 int ts_min_units();    // AO_B200_TS_MIN_UNITS (bring-up): minimum chunks per CTA of ts_gemm.cuh grids, 0 = by problem size

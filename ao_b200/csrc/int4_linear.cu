@@ -187,7 +187,7 @@ static int make_maps(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
 template <int N_MMA, int DBUF = 2>
 static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata, const uint16_t* sz, int g, int N,
                      const uint16_t* bias, uint16_t* y, int N_out, void* ws, size_t ws_bytes,
-                     const ao_linear_extras* ex, cudaStream_t stream) {
+                     cudaStream_t stream) {
   using C = tsg::Cfg<N_MMA, DBUF>;
   const int KT = K / 128;
   CUtensorMap tm_w, tm_sz, tm_x;
@@ -201,20 +201,6 @@ static int launch_tc(const uint16_t* x, int ldx, int M, int K, const int32_t* qd
   p.KT = KT;
   int grid = 0;
   if (int rc = tsg::plan<N_MMA>(p, ws, ws_bytes, "int4 linear", &grid)) return rc;
-  if (ex && prefetch_next_mode() > 0) {
-    p.pf_mode = prefetch_next_mode();
-    const size_t cap = prefetch_next_cap_bytes();   // bring-up: total bytes per launch (0 = everything)
-    size_t total = 0;
-    for (int i = 0; i < 2; ++i) total += ex->prefetch_ptr[i] ? ex->prefetch_bytes[i] : 0;
-    for (int i = 0; i < 2; ++i) {
-      if (ex->prefetch_ptr[i] && (reinterpret_cast<uintptr_t>(ex->prefetch_ptr[i]) & 15) == 0 && ex->prefetch_bytes[i] < ((size_t)1 << 32)) {
-        size_t nbytes = ex->prefetch_bytes[i];
-        if (cap && total > cap) nbytes = (size_t)((double)nbytes * (double)cap / (double)total);
-        p.pf_ptr[i] = reinterpret_cast<const uint8_t*>(ex->prefetch_ptr[i]);
-        p.pf_bytes[i] = (unsigned int)(nbytes & ~(size_t)127);
-      }
-    }
-  }
   // bring-up timeline: two slots (consecutive launches alternate) of 100 CTAs x 16 stamps + 8 chunks x 8 fine stamps at workspace + 20 MiB
   static unsigned tl_launch = 0;
   p.timeline = timeline_enabled() ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + ((size_t)20 << 20) +
@@ -252,11 +238,11 @@ static int launch_prefill(const uint16_t* x, int ldx, int M, int K, const int32_
 }  // namespace int4k
 }  // namespace ao
 
-extern "C" int ao_int4_tilepacked_linear_ex(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
-                                            const uint16_t* scale_and_zero, int group_size, int N,
-                                            const uint16_t* bias, uint16_t* y, int N_out,
-                                            void* workspace, size_t workspace_bytes, int impl,
-                                            const ao_linear_extras* extras, void* stream) {
+extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
+                                                 const uint16_t* scale_and_zero, int group_size, int N,
+                                                 const uint16_t* bias, uint16_t* y, int N_out,
+                                                 void* workspace, size_t workspace_bytes, int impl,
+                                                 void* stream) {
   using namespace ao;
   AO_REQUIRE(M >= 0 && K > 0 && N > 0, "int4 linear: bad sizes M=%d K=%d N=%d", M, K, N);
   AO_REQUIRE(K % 1024 == 0, "int4 linear: K=%d must be a multiple of 1024 (format pads K)", K);
@@ -281,27 +267,18 @@ extern "C" int ao_int4_tilepacked_linear_ex(const uint16_t* x, int ldx, int M, i
   }
   if (M <= 16)
     return int4k::launch_tc<16>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, extras, st);
+                                workspace_bytes, st);
   if (M <= 32)
     return int4k::launch_tc<32>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, extras, st);
+                                workspace_bytes, st);
   if (M <= 64)
     return int4k::launch_tc<64>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                workspace_bytes, extras, st);
+                                workspace_bytes, st);
   if (M <= 128 || prefill_disabled())
     return int4k::launch_tc<128>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                 workspace_bytes, extras, st);
+                                 workspace_bytes, st);
   return int4k::launch_prefill(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                workspace_bytes, st);
-}
-
-extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
-                                                 const uint16_t* scale_and_zero, int group_size, int N,
-                                                 const uint16_t* bias, uint16_t* y, int N_out,
-                                                 void* workspace, size_t workspace_bytes, int impl,
-                                                 void* stream) {
-  return ao_int4_tilepacked_linear_ex(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
-                                      workspace_bytes, impl, nullptr, stream);
 }
 
 extern "C" int ao_int4_tilepacked_linear(const uint16_t* x, int M, int K, const int32_t* qdata,

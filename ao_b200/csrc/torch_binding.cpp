@@ -107,12 +107,9 @@ std::tuple<Tensor, Tensor, Tensor> int4_hqq_quantize_meta(const Tensor& w, int64
 }
 
 // x [M, K] bf16 -> y [M, n_out] bf16  (aten._weight_int4pack_mm + bias + out-feature slice)
-// next_a / next_b: packed weight buffers of the linear that runs next on this stream (L2 prefetch hint,
-// ao_linear_extras in include/ao_b200.h); any CUDA tensors, only their storage range is used
 Tensor int4_tilepacked_linear(const Tensor& x, const Tensor& qdata, int64_t group_size,
                               const Tensor& scale_and_zero, const c10::optional<Tensor>& bias,
-                              int64_t n_out, int64_t impl, const c10::optional<Tensor>& next_a,
-                              const c10::optional<Tensor>& next_b) {
+                              int64_t n_out, int64_t impl) {
   TORCH_CHECK(x.is_cuda(), "ao_b200: x must be a CUDA tensor");
   check_cuda(qdata, "qdata");
   check_cuda(scale_and_zero, "scale_and_zero");
@@ -142,16 +139,7 @@ Tensor int4_tilepacked_linear(const Tensor& x, const Tensor& qdata, int64_t grou
   if (M == 0) return y;
   Tensor ws = workspace_for(x);
   const int64_t ldx = M > 1 ? x.stride(0) : K;
-  ao_linear_extras ex{};
-  const c10::optional<Tensor>* nxt[2] = {&next_a, &next_b};
-  for (int i = 0; i < 2; ++i) {
-    if (nxt[i]->has_value() && (*nxt[i])->defined() && (*nxt[i])->is_cuda() && (*nxt[i])->is_contiguous() &&
-        (*nxt[i])->get_device() == x.get_device()) {
-      ex.prefetch_ptr[i] = (*nxt[i])->data_ptr();
-      ex.prefetch_bytes[i] = (size_t)(*nxt[i])->numel() * (*nxt[i])->element_size();
-    }
-  }
-  AO_CALL(ao_int4_tilepacked_linear_ex(bf16_ptr(x), (int)ldx, (int)M, (int)K, qdata.data_ptr<int32_t>(), bf16_ptr(scale_and_zero), (int)group_size, (int)N, bias_p, bf16_ptr_mut(y), (int)n_out, ws.data_ptr(), (size_t)ws.numel(), (int)impl, &ex, cur_stream()));
+  AO_CALL(ao_int4_tilepacked_linear_strided(bf16_ptr(x), (int)ldx, (int)M, (int)K, qdata.data_ptr<int32_t>(), bf16_ptr(scale_and_zero), (int)group_size, (int)N, bias_p, bf16_ptr_mut(y), (int)n_out, ws.data_ptr(), (size_t)ws.numel(), (int)impl, cur_stream()));
   return y;
 }
 
@@ -167,8 +155,7 @@ Tensor int4_dequant_tile4d_meta(const Tensor& qdata, const Tensor& sz, int64_t) 
   return at::empty({qdata.size(0) * 8, qdata.size(1) * 128}, sz.options());
 }
 Tensor int4_tilepacked_linear_meta(const Tensor& x, const Tensor& qdata, int64_t, const Tensor&,
-                                   const c10::optional<Tensor>&, int64_t n_out, int64_t, const c10::optional<Tensor>&,
-                                   const c10::optional<Tensor>&) {
+                                   const c10::optional<Tensor>&, int64_t n_out, int64_t) {
   if (n_out <= 0) n_out = qdata.size(0) * 8;
   return at::empty({x.size(0), n_out}, x.options());
 }
@@ -182,7 +169,7 @@ TORCH_LIBRARY(ao_b200, m) {
   m.def("int4_unpack_tile4d(Tensor qdata) -> Tensor");
   m.def("int4_dequant_tile4d(Tensor qdata, Tensor scale_and_zero, int group_size) -> Tensor");
   m.def("int4_hqq_quantize(Tensor w, int group_size) -> (Tensor, Tensor, Tensor)");
-  m.def("int4_tilepacked_linear(Tensor x, Tensor qdata, int group_size, Tensor scale_and_zero, Tensor? bias, int n_out=0, int impl=0, Tensor? next_a=None, Tensor? next_b=None) -> Tensor");
+  m.def("int4_tilepacked_linear(Tensor x, Tensor qdata, int group_size, Tensor scale_and_zero, Tensor? bias, int n_out=0, int impl=0) -> Tensor");
   m.def("launch_count() -> int", []() -> int64_t { return (int64_t)ao_b200_launch_count(); });
   m.def("debug_workspace(Tensor like) -> Tensor", [](const at::Tensor& like) { return workspace_for(like); });
   ao_b200_define_lowp(m);

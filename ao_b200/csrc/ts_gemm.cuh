@@ -22,7 +22,10 @@
 //                  activation TMA producer (after griddepcontrol.wait), warp 13 MMA issuer
 //   * the weight stream is what the kernel is made of, and it depends on nothing: a CTA that is resident under the
 //     previous kernel (PDL) fills its ring while it waits for its activations.  (An L2 prefetch ahead of the ring --
-//     cp.async.bulk.prefetch.tensor -- was measured neutral to slightly negative and removed: profiles/r02_call_b.log)
+//     cp.async.bulk.prefetch.tensor -- was measured neutral to slightly negative and removed: profiles/r02_call_b.log.
+//     So was prefetching the NEXT linear's packed weights into L2 from this kernel's tail, by cp.async.bulk.prefetch.L2
+//     or per-line prefetch.global.L2, whole or capped, early or late: never faster, the bulk form up to 4x slower because
+//     it queues in front of the SM's TMA loads; profiles/r02_call_l.log, r02_call_m.log, scripts/attic)
 //   * single-thread roles are WARP-UNIFORM loops with only the tcgen05 / TMA / mbarrier instruction under elect.sync
 //     (warp index through __shfl_sync so the compiler knows it is uniform): with a loop under `lane == 0` ptxas wraps
 //     every UTCHMMA / UTMALDG in an elect-broadcast loop and one thread issues an MMA only every ~52 cycles instead
@@ -101,39 +104,7 @@ struct Params {
   int prefetch;  // bring-up: L2 prefetch distance in chunks (0 = off)
   int flags;  // bring-up switches (AO_B200_TS_FLAGS, results are garbage): 1 = skip dequant arithmetic + TMEM stores, 2 = skip MMAs, 4 = no activation loads after the first ring-full
   unsigned long long* timeline;  // debug: per-CTA [16] timestamps (AO_B200_TIMELINE=1), else null
-  // packed weights / scales of the linear that runs NEXT on this stream (ao_linear_extras): L2 prefetch hint
-  const uint8_t* pf_ptr[2];
-  unsigned int pf_bytes[2];      // multiples of 128
-  int pf_mode;                   // when / how to issue them (AO_B200_PF_MODE, bring-up): bulk prefetch 1 = after the CTA's
-                                 // last TMA request, 2 = spread over its chunks, 3 = at kernel start; per-line
-                                 // prefetch.global.L2 4 = after the last TMA request, 5 = at kernel start, 6 = after the
-                                 // weight producer's last request
 };
-
-// Part `part` of `nparts` of this CTA's 1/G share of [base, base + bytes) as L2 prefetches, one piece per lane (whole
-// warp calls).
-__device__ __forceinline__ void prefetch_share_l2(const uint8_t* base, unsigned int bytes, int b, int G, int lane,
-                                                  int part = 0, int nparts = 1) {
-  if (bytes == 0) return;
-  const unsigned int gran = bytes >> 7;   // 128-byte granules
-  const unsigned int c0 = (unsigned int)(((unsigned long long)gran * b) / G), c1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
-  const unsigned int g0 = c0 + (unsigned int)(((unsigned long long)(c1 - c0) * part) / nparts);
-  const unsigned int g1 = c0 + (unsigned int)(((unsigned long long)(c1 - c0) * (part + 1)) / nparts);
-  const unsigned int per = (g1 - g0 + 31) / 32;
-  const unsigned int l0 = g0 + per * lane;
-  const unsigned int l1 = l0 + per < g1 ? l0 + per : g1;
-  if (l0 < l1) bulk_prefetch_l2(base + ((size_t)l0 << 7), (l1 - l0) << 7);
-}
-// Same share, through the load/store unit instead of the TMA unit: one prefetch.global.L2 per 128-byte line, lanes on
-// consecutive lines.  (cp.async.bulk.prefetch.L2 turned out to be slow and to queue in front of the SM's later TMA
-// loads: profiles/r02_call_l.log, mode 2.)
-__device__ __forceinline__ void prefetch_share_l2_lsu(const uint8_t* base, unsigned int bytes, int b, int G, int lane) {
-  if (bytes == 0) return;
-  const unsigned int gran = bytes >> 7;
-  const unsigned int g0 = (unsigned int)(((unsigned long long)gran * b) / G), g1 = (unsigned int)(((unsigned long long)gran * (b + 1)) / G);
-  for (unsigned int g = g0 + lane; g < g1; g += 32)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)g << 7)) : "memory");
-}
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -518,22 +489,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         kc += np;
         if (kc >= p.KT) { kc -= p.KT; if (++n_tile == p.n_tiles) n_tile = 0; }
       }
-      if (p.pf_mode == 6 && pi == 0) {   // (bring-up) LSU prefetch a ring depth earlier than mode 4
-        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
-      }
       pdl_wait();   // idle from here on: be ready to help with the last segment's outputs
     } else if (warp == XTMA_WARP) {
       // ---------------------------------------------------------- activation producer
       const uint64_t pol_x = policy_evict_last();
-      if (p.pf_mode == 3) {
-        prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-        prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
-      }
-      if (p.pf_mode == 5) {
-        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
-      }
       pdl_wait();   // activations are the previous kernel's output
       if (lane == 0) stamp(2);
       int c = 0, cph = 1, kc = kc_of(0), tile = tile_of(0);   // cph: parity of the slot's PREVIOUS use
@@ -552,23 +511,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           }
         }
         __syncwarp();
-        if (p.pf_mode == 2) {
-          prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane, i, nunits);
-          prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane, i, nunits);
-        }
         if (++c == SX) { c = 0; cph ^= 1; }
         if (++kc == p.KT) { kc = 0; ++tile; }
-      }
-      // Every TMA request of this CTA is out (the weight producers finished a ring depth earlier): HBM would now idle
-      // through this kernel's tail and the dependent-launch gap.  Issue this CTA's share of the NEXT linear's packed
-      // weights as L2 prefetches instead (hint from the launcher, ao_linear_extras).
-      if (p.pf_mode == 1) {
-        prefetch_share_l2(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-        prefetch_share_l2(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
-      }
-      if (p.pf_mode == 4) {
-        prefetch_share_l2_lsu(p.pf_ptr[0], p.pf_bytes[0], b, G, lane);
-        prefetch_share_l2_lsu(p.pf_ptr[1], p.pf_bytes[1], b, G, lane);
       }
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer

@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-__all__ = ["fuse_parallel_linears", "FusedLinearMember", "cat_out_features", "DEFAULT_GROUPS", "chain_weight_prefetch"]
+__all__ = ["fuse_parallel_linears", "FusedLinearMember", "cat_out_features", "DEFAULT_GROUPS"]
 
 DEFAULT_GROUPS: Tuple[Tuple[str, ...], ...] = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"))
 
@@ -195,43 +195,3 @@ def fuse_parallel_linears(model: nn.Module, groups: Iterable[Sequence[str]] = DE
             fused += 1
     return fused
 
-
-def chain_weight_prefetch(model: nn.Module, wrap: bool = True) -> int:
-    """Tell every int4 linear launch which packed weights are streamed NEXT, so its kernel can prefetch them into L2.
-
-    A decode-sized linear is a few microseconds of weight streaming followed by a dependent-launch gap (the next kernel
-    cannot read its activations before this one has completed) during which HBM idles; B200's L2 holds 126 MB, more
-    than any single Llama projection.  With the link in place each CTA of linear i issues its share of linear i+1's
-    packed bytes as ``cp.async.bulk.prefetch.L2`` the moment its own last weight tile has been requested
-    (csrc/ts_gemm.cuh, ``ao_linear_extras`` in include/ao_b200.h), so HBM keeps streaming through the gap and linear
-    i+1 finds its weights on chip.  A pure hint: results are unchanged, linears without a link behave as before.
-
-    Launch order = module registration order (q|k|v, o, gate|up, down for a Llama block; fused groups from
-    ``fuse_parallel_linears`` count once); with ``wrap`` the last linear points at the first one (the next decode
-    step).  Returns the number of links made.  Call after ``quantize_`` / ``fuse_parallel_linears`` and after the model
-    is on its device."""
-    from ao_b200.quantization import Int4TilePackedTo4dTensor
-
-    units = []
-    seen = set()
-    for m in model.modules():
-        if not isinstance(m, nn.Linear):
-            continue
-        t = m._group.weight if isinstance(m, FusedLinearMember) else m.weight   # the object F.linear is called with
-        if isinstance(t, Int4TilePackedTo4dTensor) and t.is_cuda and id(t) not in seen:
-            seen.add(id(t))
-            units.append(t)
-    if len(units) < 2:
-        return 0
-    n = 0
-    for i, t in enumerate(units):
-        j = i + 1
-        if j == len(units):
-            if not wrap:
-                t._prefetch_next = None
-                continue
-            j = 0
-        nxt = units[j]
-        t._prefetch_next = (nxt.qdata, nxt.scale_and_zero)
-        n += 1
-    return n

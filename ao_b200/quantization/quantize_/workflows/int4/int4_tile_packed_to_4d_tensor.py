@@ -123,11 +123,8 @@ def _(func, types, args, kwargs):
         y = act.new_empty(act.shape[0], n_out)
     else:
         # one fused kernel: GEMM + out-feature slice + bias (the reference runs them separately)
-        # (the packed buffers of the linear that runs next, when ao_b200.fusion.chain_weight_prefetch linked them:
-        # an L2 prefetch hint for the kernel, see include/ao_b200.h ao_linear_extras)
-        nxt = getattr(weight_tensor, "_prefetch_next", None) or (None, None)
         y = torch.ops.ao_b200.int4_tilepacked_linear(act, weight_tensor.qdata, weight_tensor.block_size[-1],
-                                                     weight_tensor.scale_and_zero, bias, n_out, 0, nxt[0], nxt[1])
+                                                     weight_tensor.scale_and_zero, bias, n_out, 0)
     y = y.reshape(*orig_act_size[:-1], n_out)
     return y.to(orig_dtype)
 

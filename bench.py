@@ -247,11 +247,6 @@ def run_ours(args):
 
         bcast_bytes = broadcast_packed_weights(model, src=0)  # the one collective of the whole job
         torch.cuda.synchronize()
-    pf_links = 0
-    if not args.no_prefetch_next:
-        from ao_b200.fusion import chain_weight_prefetch
-
-        pf_links = chain_weight_prefetch(model)   # every launch prefetches the next launch's packed weights into L2
 
     def measure(bs, with_e2e=True, clocks=False):
         gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -340,7 +335,6 @@ def run_ours(args):
     cfg.update({"timing": "CUDA events over CUDA-graph replays, max over ranks", "weight_broadcast_bytes": bcast_bytes,
                 "launches_per_layer": main["launches"] // layers,
                 "fused_parallel_linears": not args.no_fuse,
-                "next_weight_l2_prefetch_links": pf_links,
                 "bs1": {"value": world / (bs1["ms"] * 1e-3), "unit": "tok/s", "ms_per_step": bs1["ms"],
                         "e2e_value": world / (bs1["ms_e2e"] * 1e-3), "roofline_frac": ab1 / (bs1["ms"] * 1e-3) / 1e9 / peak}})
     out = {
@@ -783,8 +777,6 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only: skip gpu_reference and the other configs")
     ap.add_argument("--no-fuse", action="store_true", help="7 launches per layer (q, k, v, gate, up not fused)")
-    ap.add_argument("--no-prefetch-next", action="store_true",
-                    help="do not link each linear to the next one's packed weights (ao_b200.fusion.chain_weight_prefetch)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

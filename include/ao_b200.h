@@ -93,22 +93,6 @@ int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int M, int K, 
                                       const uint16_t* bias, uint16_t* y, int N_out,
                                       void* workspace, size_t workspace_bytes, int impl,
                                       void* stream);
-/* Optional extras of a linear call.  prefetch_*: the packed weights (and scales) of the linear that runs NEXT on this
- * stream.  A decode-sized linear is a few microseconds of weight streaming followed by a dependent-launch bubble in
- * which HBM would idle; when given, every CTA issues its 1/grid share of these byte ranges as an L2 prefetch
- * (cp.async.bulk.prefetch.L2) the moment its own weight stream has been requested, so the next linear finds its weights
- * in the 126 MB L2.  Pure hint: results never depend on it.  Ranges must be 16-byte aligned; sizes are rounded down to
- * 128 bytes.  (No reference counterpart: the reference's kernels are separate library launches.)                  */
-typedef struct ao_linear_extras {
-  const void* prefetch_ptr[2];
-  size_t prefetch_bytes[2];
-} ao_linear_extras;
-int ao_int4_tilepacked_linear_ex(const uint16_t* x, int ldx, int M, int K, const int32_t* qdata,
-                                 const uint16_t* scale_and_zero, int group_size, int N,
-                                 const uint16_t* bias, uint16_t* y, int N_out,
-                                 void* workspace, size_t workspace_bytes, int impl,
-                                 const ao_linear_extras* extras, void* stream);
-
 /* int8 dynamic activation x int8 weight --------------------------------------- */
 /* Per-token symmetric int8 quantisation of activations: replaces
  * Int8Tensor.from_hp(x, PerRow()) on the hot path (int8_tensor.py:176-248 via

@@ -3,8 +3,7 @@
 fused (4 launches / layer, concatenated weights, strided slices) or unfused (7 launches / layer).
 LAYERS distinct weight sets (>> L2) so a replay never finds weights in L2.
 
-  python scripts/gpu_int4_layer.py one [fused|unfused|pf] [M,...]  # one process, current environment (pf = fused + every
-                                                                   # launch prefetches the next launch's weights into L2)
+  python scripts/gpu_int4_layer.py one [fused|unfused] [M,...]     # one process, current environment
   python scripts/gpu_int4_layer.py sweep                           # subprocess per environment setting
   python scripts/gpu_int4_layer.py shapes                          # per-shape chains (24 distinct weights each)
 """
@@ -54,20 +53,14 @@ def time_graph(fn, iters=10):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
-def layer_chain(ops, fused, M, prefetch_next=False):
+def layer_chain(ops, fused, M):
     if fused:
         shapes = [(H + 2 * KV, H), (H, H), (2 * I, H), (H, I)]
     else:
         shapes = [(H, H), (KV, H), (KV, H), (H, H), (I, H), (I, H), (H, I)]
     layers = [[mk(n, k) for n, k in shapes] for _ in range(LAYERS)]
     x0 = (torch.randn(M, H, device="cuda") * 0.5).to(torch.bfloat16)
-    # launch order -> the weights that stream next (wraps to the first linear: the next replay / decode step)
-    flat = [w for L in layers for w in L]
-    nxt = {id(w): flat[(i + 1) % len(flat)] for i, w in enumerate(flat)}
-
-    def lin(x, w):
-        n = nxt[id(w)] if prefetch_next else (None, None)
-        return ops.int4_tilepacked_linear(x, w[0], G, w[1], None, w[0].shape[0] * 8, 1, n[0], n[1])
+    lin = lambda x, w: ops.int4_tilepacked_linear(x, w[0], G, w[1], None, w[0].shape[0] * 8, 1)
 
     def fn():
         x = x0
@@ -97,7 +90,7 @@ def one(args):
     mode = args[0] if args else "fused"
     Ms = [int(v) for v in args[1].split(",")] if len(args) > 1 else [1, 32]
     for M in Ms:
-        us, nbytes = layer_chain(ops, mode != "unfused", M, prefetch_next=(mode == "pf"))
+        us, nbytes = layer_chain(ops, mode == "fused", M)
         print(f"  {mode:8s} M={M:3d}: {us:8.2f} us/layer  {nbytes/us/1e3:8.1f} GB/s  -> {us*32/1e3:6.3f} ms/step  frac {nbytes/us/1e3/6587.7:.3f}", flush=True)
 
 

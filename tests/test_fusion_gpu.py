@@ -161,49 +161,6 @@ def test_llama_layer_chain_fused_vs_unfused():
         assert _sqnr(ya, yb) > 40.0   # two layers of bf16 re-rounding between differently associated sums
 
 
-def test_next_weight_prefetch_hint_changes_nothing_but_is_wired():
-    """chain_weight_prefetch links every launch to the packed buffers of the next one (wrapping to the first); the
-    kernel only issues L2 prefetches for them, so outputs are bit-identical with and without the links, eagerly and
-    under a CUDA graph, and the op accepts the hint directly."""
-    import ao_b200  # noqa: F401
-    from ao_b200.fusion import chain_weight_prefetch, fuse_parallel_linears
-    from ao_b200.models import LlamaLinearStack, LlamaShape
-    from ao_b200.quantization import Int4WeightOnlyConfig, quantize_
-
-    shape = LlamaShape("tiny", 1024, 3072, 256, 2)
-    m = LlamaLinearStack(shape, device="cuda", seed=0, init_scale=0.05)
-    quantize_(m, Int4WeightOnlyConfig(group_size=32, int4_packing_format="tile_packed_to_4d"))
-    fuse_parallel_linears(m)
-    x = torch.randn(32, 1024, device="cuda", dtype=torch.bfloat16)
-    with torch.no_grad():
-        y0 = m(x)
-    assert chain_weight_prefetch(m) == 8            # 2 layers x (q|k|v, o, gate|up, down), last -> first
-    l0 = m.layers[0]
-    qkv, o = l0.q_proj._group.weight, l0.o_proj.weight
-    assert qkv._prefetch_next[0] is o.qdata and qkv._prefetch_next[1] is o.scale_and_zero
-    last = m.layers[-1].down_proj.weight
-    assert last._prefetch_next[0] is qkv.qdata
-    with torch.no_grad():
-        y1 = m(x)
-        g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            m(x)
-        torch.cuda.current_stream().wait_stream(s)
-        with torch.cuda.graph(g):
-            y2 = m(x)
-        g.replay()
-    torch.cuda.synchronize()
-    assert torch.equal(y0, y1) and torch.equal(y0, y2)
-    # straight through the op, with an unrelated buffer as the hint and with odd sizes (rounded down to 128 bytes)
-    ops = torch.ops.ao_b200
-    junk = torch.empty(1000003, device="cuda", dtype=torch.uint8)
-    ya = ops.int4_tilepacked_linear(x, o.qdata, 32, o.scale_and_zero, None, 1024, 1)
-    yb = ops.int4_tilepacked_linear(x, o.qdata, 32, o.scale_and_zero, None, 1024, 1, junk, junk[:48])
-    assert torch.equal(ya, yb)
-
-
 @pytest.mark.parametrize("M", [1, 5, 32, 130])
 def test_row_strided_quantizers_match_contiguous(M):
     """The activation quantizers take a column slice of a wider buffer directly: same bytes as for its contiguous copy
