@@ -364,18 +364,22 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&dempty[buf]);
     };
-    // the segment whose last chunk is e belongs to warpgroup e % 3, which runs its epilogue after its next chunk
-    int ep_seg = 0;
+    // the segment whose last chunk is e belongs to warpgroup e % 3, which runs its epilogue after its next chunk.
+    // ep_at = last chunk of the next segment (before the CTA's last one) that belongs to this warpgroup, kept outside the
+    // chunk loop: the loop itself pays one compare per chunk (the integer pipe is what the dequant warps are short of)
+    int ep_seg = 0, ep_at = 0x7fffffff;
     const bool eager0 = walk.seg_kind(0) == streamk::SEG_CONTRIB && nunits - walk.seg_count(0) < 12;
     auto seg_end = [&](int sg) { return walk.seg_begin(sg) + walk.seg_count(sg) - 1; };
+    auto next_owned = [&]() {
+      while (ep_seg < seg_last && seg_end(ep_seg) % DEQ_WGS != wg) ++ep_seg;
+      ep_at = ep_seg < seg_last ? seg_end(ep_seg) : 0x7fffffff;
+    };
+    next_owned();
     auto run_epilogues = [&](int before_chunk) {
-      while (ep_seg < seg_last) {
-        const int e = seg_end(ep_seg);
-        if (e % DEQ_WGS == wg) {
-          if (e >= before_chunk) break;
-          epilogue(ep_seg);
-        }
+      while (ep_at < before_chunk) {
+        epilogue(ep_seg);
         ++ep_seg;
+        next_owned();
       }
     };
 
@@ -400,12 +404,15 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       } else {
         typename Fmt::Raw raw;
         Fmt::load_row(p, st, st + W_BYTES, r, raw);
-        uint32_t out[16];
-        Fmt::dequant_quarter(p, raw, 0, out);
-        Fmt::touch(raw);   // every ld.shared of the row has returned (quarter 0 alone does not use all of them)
+        Fmt::touch(raw);   // every ld.shared of the row has returned
         __syncwarp();
-        if (elect_one()) mbar_arrive(&sempty[s]);  // weights are in registers: the stage can be refilled
+        // weights are in registers: the stage goes back to the producers BEFORE any arithmetic -- the ring (8 stages x
+        // 10 KB against a 3000-4500 cycle loaded DRAM round trip) is what paces the streaming phase, and every cycle a
+        // landed stage is held is added to that round trip
+        if (elect_one()) mbar_arrive(&sempty[s]);
         if (q4 == 0 && lane == 0) fstamp(i, 2);
+        uint32_t out[16];
+        Fmt::dequant_quarter(p, raw, 0, out);   // (before the A stage is known to be free: that wait overlaps arithmetic)
         if (i >= T) {
           // the first T chunks were dequantised under the previous kernel; from here on the warpgroup needs MMAs of
           // THIS kernel, which need its activations, which need the previous kernel: the dependency wait costs nothing

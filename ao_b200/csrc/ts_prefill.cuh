@@ -208,11 +208,11 @@ ts_prefill_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
       mbar_wait(&wfull[s], (i / S) & 1);
       typename Fmt::Raw raw;
       Fmt::load_row(p, st, st + W_BYTES, r, raw);
-      uint32_t out[16];
-      Fmt::dequant_quarter(p, raw, 0, out);
       Fmt::touch(raw);
       __syncwarp();
       if (elect_one()) mbar_arrive(&wempty[s]);       // the row is in registers: the stage can be refilled
+      uint32_t out[16];
+      Fmt::dequant_quarter(p, raw, 0, out);
       if (i >= T) mbar_wait(&aempty[t], ((i / T) & 1) ^ 1);   // MMAs of chunk i - T are done: A stage t is free
       tc_fence_after();
       tmem_st_x16(a_t, out);

@@ -438,7 +438,7 @@ def prefill_gemms(args, dev, peak_tf):
     ">= 70 % of the tensor-core roofline" clause applies): the four fused Llama-3-8B projections at M = 512 and 4096,
     int4 weight-only (the prefill-shaped TS kernel, csrc/ts_prefill.cuh) with the kernel the reference calls
     (aten._weight_int4pack_mm, M = 512 only: it needs tens of milliseconds at 4096) and cuBLAS bf16 (F.linear on
-    bf16 weights, what `peak_tf` was measured with) beside it; fp8-rowwise and int8-dynamic with their library kernels.
+    bf16 weights, what `peak_tf` was measured with) beside it; fp8-rowwise, int8-dynamic, mxfp8 and nvfp4 with their library kernels.
     TFLOP/s = 2 M N K / time, CUDA events over back-to-back launches on weights + activations larger than L2 for
     the big shapes; `frac` is against the measured bf16 peak (x2 for the 8-bit kinds)."""
     import torch
@@ -460,7 +460,7 @@ def prefill_gemms(args, dev, peak_tf):
         return e0.elapsed_time(e1) / iters * 1e3
 
     out = {"peak_bf16_tflops": peak_tf, "unit": "TFLOP/s", "note": "one GEMM per entry; frac = TFLOP/s over the measured bf16 "
-           "tensor peak (x2 for fp8 / int8); int4 runs ao::tsp::ts_prefill_kernel, fp8 / int8 run lowp_linear_kernel in 128-token blocks"}
+           "tensor peak (x2 for fp8 / int8 / mxfp8, x4 for nvfp4); int4 runs ao::tsp::ts_prefill_kernel, the others lowp_linear_kernel in 128-token blocks"}
     for M in (512, 4096):
         for name, N, K in shapes:
             flops = 2.0 * M * N * K
@@ -476,8 +476,21 @@ def prefill_gemms(args, dev, peak_tf):
             del qd, sz
             w = torch.randn(N, K, device=dev).to(torch.bfloat16)
             rec["bf16_cublas_us"] = t_us(lambda: torch.nn.functional.linear(x, w), 5)
-            for fmt in ("fp8", "int8"):
-                if fmt == "fp8":
+            for fmt in ("fp8", "int8", "mxfp8", "nvfp4"):
+                if fmt == "mxfp8":
+                    wq, ws = ops.mxfp8_quantize(w, True)
+                    xq, xs = ops.mxfp8_quantize(x, True)
+                    fn = lambda: ops.mxfp8_linear(xq, xs, wq, ws, None)
+                    lib = lambda: torch._scaled_mm(xq, wq.t(), scale_a=xs.view(torch.float8_e8m0fnu), scale_b=ws.view(torch.float8_e8m0fnu),
+                                                   out_dtype=torch.bfloat16)
+                elif fmt == "nvfp4":
+                    wq, ws = ops.nvfp4_quantize(w, None, True)
+                    xq, xs = ops.nvfp4_quantize(x, None, True)
+                    fn = lambda: ops.nvfp4_linear(xq, xs, None, wq, ws, None, None)
+                    lib = lambda: torch._scaled_mm(xq.view(torch.float4_e2m1fn_x2), wq.view(torch.float4_e2m1fn_x2).t(),
+                                                   scale_a=xs.view(torch.float8_e4m3fn), scale_b=ws.view(torch.float8_e4m3fn),
+                                                   out_dtype=torch.bfloat16)
+                elif fmt == "fp8":
                     wq, ws = ops.fp8_quantize_rowwise(w)
                     xq, xs = ops.fp8_quantize_rowwise(x)
                     fn = lambda: ops.fp8_rowwise_linear(xq, xs.reshape(-1), wq, ws.reshape(-1), None)
@@ -489,7 +502,12 @@ def prefill_gemms(args, dev, peak_tf):
                     fn = lambda: ops.int8_dyn_linear(xq, xs.reshape(-1), wq, ws.reshape(-1), None)
                     lib = lambda: torch._int_mm(xq, wq.t())
                 us = t_us(fn, 5)
-                rec[fmt] = {"us": us, "tflops": flops / us / 1e6, "frac": flops / us / 1e6 / (2 * peak_tf), "library_us": t_us(lib, 5)}
+                mul = 4 if fmt == "nvfp4" else 2   # dense peak of the kind relative to bf16
+                rec[fmt] = {"us": us, "tflops": flops / us / 1e6, "frac": flops / us / 1e6 / (mul * peak_tf)}
+                try:
+                    rec[fmt]["library_us"] = t_us(lib, 5)
+                except Exception as ex:  # pragma: no cover
+                    rec[fmt]["library_error"] = f"{type(ex).__name__}: {ex}"[:120]
                 del wq, ws, xq, xs
             out[f"M{M}_{name}"] = rec
             del x, w
