@@ -274,7 +274,7 @@ extern "C" int ao_int4_tilepacked_linear_strided(const uint16_t* x, int ldx, int
   if (M <= 64)
     return int4k::launch_tc<64>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                 workspace_bytes, st);
-  if (M <= 128 || prefill_disabled())
+  if (!tsp::worth_it(M, N_out, K))
     return int4k::launch_tc<128>(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,
                                  workspace_bytes, st);
   return int4k::launch_prefill(x, ldx, M, K, qdata, scale_and_zero, group_size, N, bias, y, N_out, workspace,

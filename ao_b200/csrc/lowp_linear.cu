@@ -397,14 +397,14 @@ static int launch(const uint8_t* xq, const uint8_t* x_sf, const float* x_scale, 
   p.sf_col_blocks_w = ceil_div(sf_per_row, 4);
   p.sf_col_blocks_x = ceil_div(sf_per_row, 4);
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
-  // one CTA per SM, but never fewer than ~4 chunks per CTA (tiny GEMMs are launch/fix-up bound otherwise)
-  // (8 when more than 8 token columns are reduced: finer splits lengthen the split-tile reduction more than they
-  // shorten the streaming phase)
+  // never fewer than 8 chunks per CTA: finer splits lengthen the split-tile reduction more than they shorten the
+  // streaming phase (fp8, q|k|v projection: 12.6 -> 10.5 us at 1 token, 15.2 -> 13.5 us at 32 with 8 instead of 4; 16 is
+  // worse again: profiles/r02_call_p.log)
   // two CTAs per SM where they fit (N_MMA <= 64): this kernel has no dequant phase, it is bounded by the bytes in
   // flight per SM (stages x 16-20 KB against the DRAM round trip), which a second resident CTA doubles
   const int per_sm = (N_MMA <= 64) ? (ts_ctas_per_sm() ? ts_ctas_per_sm() : 2) : 1;
   int grid = sm_count() * per_sm;
-  const int min_units = ts_min_units() ? ts_min_units() : 4;
+  const int min_units = ts_min_units() ? ts_min_units() : 8;
   if (units / min_units < grid) grid = units / min_units > 0 ? (int)(units / min_units) : 1;
   const size_t need = streamk::WS_PARTIAL_OFF + (size_t)grid * N_MMA * ROWS * 4;
   if (!ws || ws_bytes < need || (size_t)grid * 4 > streamk::WS_FLAGS_BYTES)

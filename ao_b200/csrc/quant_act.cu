@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256, 3) quant_rowwise_reg_kernel(const __nv_bf
 //                                                                                  cast to the input dtype, * weight)
 //   PRO 2  SiLU-mul  y = bf16(bf16(silu_f32(g)) * u)                              (HF LlamaMLP: act_fn(gate) * up)
 // followed by exactly quant_rowwise_kernel's arithmetic on y (MODE 0 int8 per token, MODE 1 e4m3 per token).  One
-// CTA per token; the row of y is kept in shared memory between the abs-max pass and the cast pass.
+// CTA per token; the row of y is kept in shared memory between the abs-max pass and the cast pass.  (A register-resident
+// variant like quant_rowwise_reg_kernel was measured SLOWER here -- 128 registers, two CTAs per SM: 2.0 / 1.4 TB/s against
+// 2.5 / 2.6 TB/s, profiles/r02_call_p.log -- and removed.)
 __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -296,131 +298,6 @@ __global__ void __launch_bounds__(256) fused_rowwise_kernel(const __nv_bfloat16*
       }
     }
     qr[i] = *reinterpret_cast<const uint2*>(o);
-  }
-}
-
-// Register-resident version of fused_rowwise_kernel (K <= 16384): like quant_rowwise_reg_kernel the row never leaves the
-// registers between its passes (RMSNorm: sum of squares -> normalised row -> abs-max -> cast; SiLU-mul: product -> abs-max
-// -> cast), `tpr` threads per row, 256 / tpr rows per CTA, every global load issued before the first use.
-__device__ __forceinline__ float row_reduce(float v, float* sh, int tpr, int row_in_cta, bool is_max) {
-  for (int o = 16; o > 0; o >>= 1) {
-    const float t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? fmaxf(v, t) : v + t;
-  }
-  if (tpr > 32) {   // (uniform) the row spans tpr / 32 warps
-    const int w = threadIdx.x >> 5;
-    __syncthreads();   // the previous reduction's readers are done with sh
-    if ((threadIdx.x & 31) == 0) sh[w] = v;
-    __syncthreads();
-    const int w0 = row_in_cta * (tpr >> 5);
-    v = sh[w0];
-    for (int i = 1; i < (tpr >> 5); ++i) v = is_max ? fmaxf(v, sh[w0 + i]) : v + sh[w0 + i];
-  }
-  return v;
-}
-
-template <int MODE, int PRO>
-__global__ void __launch_bounds__(256, 2) fused_rowwise_reg_kernel(const __nv_bfloat16* __restrict__ a, int lda,
-                                                                   const __nv_bfloat16* __restrict__ b, int ldb, float eps,
-                                                                   int M, int K, int tpr, uint8_t* __restrict__ q,
-                                                                   float* __restrict__ scale) {
-  constexpr int VPT = 8;
-  __shared__ float sh[8];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int row_in_cta = threadIdx.x / tpr, t = threadIdx.x % tpr;
-  const int m = blockIdx.x * (256 / tpr) + row_in_cta;
-  const bool active = m < M;
-  const int nv = K / 8;
-  const uint4* ar = reinterpret_cast<const uint4*>(a + (size_t)(active ? m : 0) * lda);
-  const uint4* br = reinterpret_cast<const uint4*>(PRO == 1 ? b : b + (size_t)(active ? m : 0) * ldb);   // weight[K] or up[m, :]
-  uint4 va[VPT], vb[VPT];
-#pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const int i = t + j * tpr;
-    const bool ok = active && i < nv;
-    va[j] = ok ? ar[i] : make_uint4(0u, 0u, 0u, 0u);
-    vb[j] = ok ? br[i] : make_uint4(0u, 0u, 0u, 0u);
-  }
-  float rstd = 0.f;
-  if (PRO == 1) {
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&va[j]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h[e]);
-        ss += f.x * f.x + f.y * f.y;
-      }
-    }
-    ss = row_reduce(ss, sh, tpr, row_in_cta, false);
-    rstd = rsqrtf(ss / (float)K + eps);
-  }
-  // y (bf16) replaces a in the registers
-  float amax = 0.f;
-#pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&va[j]);
-    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&vb[j]);
-    uint4 out;
-    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
-      float y0, y1;
-      if (PRO == 1) {
-        y0 = bf16_round(fb.x * bf16_round(fa.x * rstd));
-        y1 = bf16_round(fb.y * bf16_round(fa.y * rstd));
-      } else {
-        y0 = bf16_round(bf16_round(fa.x / (1.f + expf(-fa.x))) * fb.x);
-        y1 = bf16_round(bf16_round(fa.y / (1.f + expf(-fa.y))) * fb.y);
-      }
-      ho[e] = __floats2bfloat162_rn(y0, y1);
-      amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
-    }
-    va[j] = out;
-  }
-  amax = row_reduce(amax, sh, tpr, row_in_cta, true);
-  float s;
-  if (MODE == 0) s = fmaxf(bf16_round(amax / 127.5f), 1.1920928955078125e-07f);
-  else s = bf16_round(amax / 448.0f);
-  if (active && t == 0) scale[m] = s;
-  const float inv = 1.0f / s;
-  uint2* qr = reinterpret_cast<uint2*>(q + (size_t)(active ? m : 0) * K);
-#pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const int i = t + j * tpr;
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&va[j]);
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t2 = __bfloat1622float2(h[e]);
-      f[2 * e] = t2.x;
-      f[2 * e + 1] = t2.y;
-    }
-    uint2 o;
-    if (MODE == 0) {
-      o.x = pack_s8x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-      o.y = pack_s8x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
-    } else {
-      if (s >= 0x1p-64f && s <= 0x1p64f) {   // (see quant_rowwise_reg_kernel: exact quotient by reciprocal + one FMA residual)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float q0 = f[e] * inv;
-          f[e] = fminf(fmaxf(fmaf(fmaf(-q0, s, f[e]), inv, q0), -448.f), 448.f);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f[e] = fminf(fmaxf(f[e] / s, -448.f), 448.f);
-          if (s == 0.f) f[e] = __int_as_float(0x7fc00000);   // 0/0 = NaN in the reference
-        }
-      }
-      o.x = pack_e4m3x4(f[0], f[1], f[2], f[3]);
-      o.y = pack_e4m3x4(f[4], f[5], f[6], f[7]);
-    }
-    if (active && i < nv) qr[i] = o;
   }
 }
 
@@ -593,14 +470,6 @@ using namespace ao;
 
 template <int MODE, int PRO>
 static int launch_fused(const uint16_t* a, int lda, const uint16_t* b, int ldb, float eps, int M, int K, uint8_t* q, float* scale, void* stream) {
-  if (K <= 16384) {
-    int tpr = 32;
-    while (tpr * 64 < K) tpr *= 2;
-    AO_CUDA_CHECK(ao::launch(fused_rowwise_reg_kernel<MODE, PRO>, dim3((unsigned)ceil_div(M, 256 / tpr)), dim3(256), 0,
-                             reinterpret_cast<cudaStream_t>(stream), pdl_enabled(), reinterpret_cast<const __nv_bfloat16*>(a), lda,
-                             reinterpret_cast<const __nv_bfloat16*>(b), ldb, eps, M, K, tpr, q, scale));
-    return AO_OK;
-  }
   auto kern = fused_rowwise_kernel<MODE, PRO>;
   const size_t smem = (size_t)K * 2;
   AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), 96 * 1024));

@@ -319,6 +319,17 @@ ts_prefill_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
   }
 }
 
+// When to take this kernel instead of the decode kernel's 128-token blocks (M > 128): measured crossover on the
+// Llama-3-8B projections (profiles/r02_call_q.log).  With fewer than ~50 chunks of 128 x 256 per SM the 128-token-block
+// path is ahead (smaller tiles split more evenly, 16 KB instead of 128 KB of partials per split tile): e.g. 512 tokens,
+// o-proj 23.2 vs 30.1 us, down-proj 49.6 vs 55.4 us; above it this kernel wins by up to 16 % (4096 tokens, gate|up 715 vs
+// 832 us).
+inline bool worth_it(int M, int N_out, int K) {
+  if (M <= 128 || prefill_disabled()) return false;
+  const long long units = (long long)ceil_div(N_out, ROWS) * ceil_div(M, N_TOK) * (K / KCHUNK);
+  return units >= 50LL * sm_count();
+}
+
 // Grid + workspace carve-up: one CTA per SM, never fewer than 8 chunks per CTA.
 inline int plan(tsg::Params& p, void* ws, size_t ws_bytes, const char* what, int* grid_out) {
   const long long units = (long long)p.n_tiles * p.m_blocks * p.KT;
