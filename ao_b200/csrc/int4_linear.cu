@@ -73,10 +73,14 @@ struct Int4Fmt {
       raw.v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 7) << 4)));  // undo the TMA 128B swizzle
     }
   }
-  __device__ static __forceinline__ void touch(const Raw& raw) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) asm volatile("" ::"r"(raw.v[i].x), "r"(raw.v[i].y), "r"(raw.v[i].z), "r"(raw.v[i].w));
-    asm volatile("" ::"r"(raw.sz[0]), "r"(raw.sz[1]), "r"(raw.sz[2]), "r"(raw.sz[3]));
+  // A value that depends on one destination register of EVERY ld.shared of load_row.  The kernels fold it into the
+  // address of the mbarrier arrive that hands the stage back to the TMA producers (through a comparison that is never
+  // true at run time but that ptxas cannot decide), so the arrive cannot issue before the loads have returned.  Without a
+  // data dependence it does: an empty asm with "r" inputs emits nothing, an unused xor chain is removed by ptxas, the
+  // arrive overtakes the loads in flight and the refill races with them (round 2: 2 of 6 runs of the nvfp4-weight prefill
+  // test off by a few values, profiles/r02_call_s.log).
+  __device__ static __forceinline__ uint32_t touch(const Raw& raw) {
+    return raw.v[0].x ^ raw.v[1].x ^ raw.v[2].x ^ raw.v[3].x ^ raw.sz[0] ^ raw.sz[1] ^ raw.sz[2] ^ raw.sz[3];
   }
   // quarter q = the 32 k of tinygemm word q: out[c] = bf16x2 of k pair (32q + 2c, 32q + 2c + 1), c = i + 4e
   __device__ static __forceinline__ void dequant_quarter(const tsg::Params&, const Raw& raw, int q, uint32_t (&out)[16]) {

@@ -59,10 +59,9 @@ struct Nvfp4Fmt {
       raw.v[i] = tsg::lds128(w_smem + (off ^ (((off >> 7) & 3) << 4)));  // undo the TMA 64B swizzle
     }
   }
-  __device__ static __forceinline__ void touch(const Raw& raw) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) asm volatile("" ::"r"(raw.v[i].x), "r"(raw.v[i].y), "r"(raw.v[i].z), "r"(raw.v[i].w));
-    asm volatile("" ::"r"(raw.sc[0]), "r"(raw.sc[1]));
+  // depends on one destination register of every ld.shared of load_row (see Int4Fmt::touch)
+  __device__ static __forceinline__ uint32_t touch(const Raw& raw) {
+    return raw.v[0].x ^ raw.v[1].x ^ raw.v[2].x ^ raw.v[3].x ^ raw.sc[0] ^ raw.sc[1];
   }
   // quarter q = bytes 16q..16q+15 of the row = k 32q..32q+31: out[c] = bf16x2 of k pair (32q + 2c, +1)
   __device__ static __forceinline__ void dequant_quarter(const tsg::Params&, const Raw& raw, int q, uint32_t (&out)[16]) {
