@@ -162,7 +162,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   uint64_t* dempty = dfull + 2;       // [2]   the 4 warps of the warpgroup that ran the segment's epilogue
   uint64_t* dlast = dempty + 2;       // [1]   accumulator of the CTA's LAST segment complete (single phase: any warp
                                       //       may wait on it without having followed the dfull phases)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dlast + 1);
+  uint64_t* fok = dlast + 1;          // [1]   the contributors' flags of an OWNER last segment have been seen (one poller)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fok + 1);
 
   // The warp index goes through a shuffle so that the compiler knows it is warp-uniform: the single-thread
   // roles below run as warp-uniform loops with only the tcgen05 / TMA / mbarrier instruction itself under
@@ -205,6 +206,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_init(&dempty[i], 4);
     }
     mbar_init(dlast, 1);
+    mbar_init(fok, 1);
     fence_barrier_init();
   }
   if (warp == TMA_WARP && lane == 0) {
@@ -258,7 +260,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const float bias = (p.bias && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
     const float osc = p.out_scale ? (p.out_scale_per_row ? (row_ok ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f;
     const float* slot0 = p.ws_partial + (size_t)(b + 1) * (N_MMA * ROWS) + r;
-    streamk::wait_flags(p.ws_flag + b + 1, n_oth, lane);
+    // the contributors' flags were seen by the activation-producer warp (ld.acquire.gpu, then this cta-scope barrier):
+    // its L2 round trip -- ~0.8 us even when the flags were raised long ago -- runs under the last MMAs instead of
+    // between them and the gather
+    mbar_wait(fok, 0);
     if (helper == 0 && r == 0) stamp(8);
     if (p.M - m0 == 1) {
       // decode, one token column: every contributor's value in flight at once
@@ -521,6 +526,18 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         __syncwarp();
         if (++c == SX) { c = 0; cph ^= 1; }
         if (++kc == p.KT) { kc = 0; ++tile; }
+      }
+      if (last_kind == streamk::SEG_OWNER) {
+        // this warp's work is done a few chunks before the CTA's: it becomes the ONE poller of the contributors' flags
+        // (sixteen warps polling global memory from here was measured 15 % slower per layer, profiles/r02_call_s.log)
+        const int b_last = streamk::cta_of_unit((long long)last_tile * p.KT + p.KT - 1, U, G);
+        const int n_oth = b_last - b;
+        for (int base = 0; base < n_oth; base += 32)
+          if (base + lane < n_oth)
+            while (streamk::ld_acquire_u32(p.ws_flag + b + 1 + base + lane) == 0u) __nanosleep(64);
+        __syncwarp();
+        if (elect_one()) mbar_arrive(fok);
+        __syncwarp();
       }
     } else if (warp == MMA_WARP) {
       // ---------------------------------------------------------- MMA issuer
