@@ -86,7 +86,8 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   uint64_t* sempty = xfull + S;      // [S] MMA commit
   uint64_t* dfull = sempty + S;      // [2]
   uint64_t* dempty = dfull + 2;      // [2] 4 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  uint64_t* fok = dempty + 2;        // [1] the contributors' flags of an OWNER last segment have been seen (TMA warp polls)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fok + 1);
 
   // warp index through a shuffle => known warp-uniform: the single-thread roles are warp-uniform loops with only
   // the TMA / tcgen05 instructions under elect.sync, so their operands live in uniform registers (with the whole
@@ -110,6 +111,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], 4);
     }
+    mbar_init(fok, 1);
     fence_barrier_init();
   }
   if (warp == TMA_WARP && lane == 0) {
@@ -172,6 +174,19 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           issue_w(i);
           issue_x(i);
         }
+        __syncwarp();
+      }
+      if (walk.seg_kind(walk.nseg - 1) == streamk::SEG_OWNER) {
+        // this warp is done a ring depth before the CTA is: it polls the contributors' flags (ld.acquire.gpu) and passes
+        // the result on through a cta-scope barrier, so that L2 round trip runs under the last MMAs instead of between
+        // them and the owner's gather (same scheme as ts_gemm.cuh)
+        const int tile_l = walk.seg_tile(walk.nseg - 1);
+        const int n_oth = cta_of_unit((long long)tile_l * p.KT + p.KT - 1, U, G) - b;
+        for (int base = 0; base < n_oth; base += 32)
+          if (base + lane < n_oth)
+            while (streamk::ld_acquire_u32(p.ws_flag + b + 1 + base + lane) == 0u) __nanosleep(64);
+        __syncwarp();
+        if (elect_one()) mbar_arrive(fok);
         __syncwarp();
       }
     }
@@ -302,7 +317,7 @@ lowp_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         const int b_last = cta_of_unit((long long)tile * p.KT + p.KT - 1, U, G);
         const int n_oth = b_last - b;
         const uint32_t* slot0 = reinterpret_cast<const uint32_t*>(p.ws_partial) + (size_t)(b + 1) * (N_MMA * ROWS) + r;
-        streamk::wait_flags(p.ws_flag + b + 1, n_oth, lane);
+        mbar_wait(fok, 0);   // flags seen by the TMA warp (above)
 #pragma unroll 1
         for (int j0 = 0; j0 < N_MMA; j0 += 16) {
           if (m0 + j0 >= p.M) break;
