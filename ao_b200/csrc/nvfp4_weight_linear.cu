@@ -29,20 +29,17 @@ using tsg::W_BYTES;
 
 struct Nvfp4Fmt {
   __device__ static __forceinline__ uint32_t w_tx_bytes(const tsg::Params&) { return W_BYTES + 1024; }
-  __device__ static __forceinline__ void issue_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p,
+  __device__ static __forceinline__ void issue_w(const CUtensorMap* tm_w, const CUtensorMap* tm_sf, const tsg::Params& p,
                                                  uint8_t* w_dst, uint8_t* aux_dst, uint64_t* bar, int n_tile, int kc,
                                                  uint64_t policy) {
     tma_load_2d(w_dst, tm_w, bar, kc * 64, n_tile * ROWS, policy);  // 128 rows x 64 bytes, 64B swizzle
-    // two consecutive blocked scale tiles (128 rows x 4 scales each = 64 k per tile)
-    const uint8_t* src = p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(aux_dst)),
-                 "l"(src), "r"(1024), "r"(smem_u32(bar))
-                 : "memory");
+    // two consecutive blocked scale tiles (128 rows x 4 scales each = 64 k per tile): the blocked scale tensor is a
+    // [row block][column block] array of contiguous 512-byte tiles = a 2-D tensor of 128 words x tiles
+    tma_load_2d(aux_dst, tm_sf, bar, 0, n_tile * p.aux_col_blocks + kc * 2, policy);
   }
-  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap*, const tsg::Params& p, int n_tile, int kc) {
+  __device__ static __forceinline__ void prefetch_w(const CUtensorMap* tm_w, const CUtensorMap* tm_sf, const tsg::Params& p, int n_tile, int kc) {
     tma_prefetch_l2_2d(tm_w, kc * 64, n_tile * ROWS);
-    bulk_prefetch_l2(p.aux_base + ((size_t)n_tile * p.aux_col_blocks + (size_t)kc * 2) * 512, 1024);
+    tma_prefetch_l2_2d(tm_sf, 0, n_tile * p.aux_col_blocks + kc * 2);
   }
   // one weight row of the chunk: its 64 bytes (k 0..127, even k in the low nibble) and the 8 block scales
   struct Raw {
@@ -104,6 +101,14 @@ static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, in
     int rc = make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wq, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
+  CUtensorMap tm_sf;
+  {
+    const uint64_t dims[2] = {128, (uint64_t)ceil_div(N, ROWS) * (uint64_t)ceil_div(K / 16, 4)};
+    const uint64_t str[1] = {512};
+    const uint32_t box[2] = {128, 2};
+    int rc = make_tmap(&tm_sf, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, w_sf, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)ldx * 2};
@@ -128,14 +133,14 @@ static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, in
     if (int rc = tsp::plan(p, ws, ws_bytes, "nvfp4 weight linear (prefill)", &grid)) return rc;
     auto kern = tsp::ts_prefill_kernel<Nvfp4Fmt>;
     AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), tsp::SMEM_BYTES));
-    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsp::NUM_THREADS), tsp::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsp::NUM_THREADS), tsp::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_sf, tm_x, p));
   } else {
     using C = tsg::Cfg<(PREFILL ? 128 : N_MMA)>;
     if (int rc = tsg::plan<(PREFILL ? 128 : N_MMA)>(p, ws, ws_bytes, "nvfp4 weight linear", &grid)) return rc;
     p.timeline = nullptr;
     auto kern = tsg::ts_gemm_kernel<Nvfp4Fmt, (PREFILL ? 128 : N_MMA)>;
     AO_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
-    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_w, tm_x, p));
+    AO_CUDA_CHECK(launch(kern, dim3(grid), dim3(tsg::NUM_THREADS), C::SMEM_BYTES, stream, pdl_enabled(), tm_w, tm_sf, tm_x, p));
   }
   return AO_OK;
 }
