@@ -9,9 +9,10 @@
 // per-tensor scale is applied in fp32 in the epilogue.
 //
 // e2m1 -> bf16 without a table: nibble x = (s e1 e0 m) placed at bf16 bits 15|8:6 is the bf16 number
-// value(x) * 2^-126 (denormal for e = 0, which bf16 multiplies handle exactly); one exact multiply by 2^120
-// and one by (block_scale * 2^6) give value(x) * block_scale.  bf16(block_scale * 64) = (byte << 4) + 0x3F00
-// for the (always normal, >= 2^-6) e4m3 scale bytes.
+// value(x) * 2^-126 (denormal for e = 0, which bf16 multiplies handle exactly); ONE exact multiply by
+// (block_scale * 2^66) gives value(x) * block_scale * 2^-60, and the 2^60 is taken back out of the fp32 accumulator in the
+// epilogue (Params::acc_exp2; power-of-two factors commute with every rounding on the way).  bf16(block_scale * 2^66) =
+// (byte << 4) + 0x5D00 for the (always normal, >= 2^-6) e4m3 scale bytes.
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 
@@ -64,26 +65,31 @@ struct Nvfp4Fmt {
   __device__ static __forceinline__ void dequant_quarter(const tsg::Params&, const Raw& raw, int q, uint32_t (&out)[16]) {
     const uint4 v = raw.v[q];
     const uint32_t sc = raw.sc[q >> 1] >> (16 * (q & 1));   // two scale bytes: blocks 2q, 2q + 1
-    const uint32_t two120 = 0x7B807B80u;  // bf16x2 of 2^120
-    const __nv_bfloat162 c120 = *reinterpret_cast<const __nv_bfloat162*>(&two120);
 #pragma unroll
     for (int w = 0; w < 4; ++w) {  // word w = k 8w..8w+7 of the quarter; scale block = w/2
       const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
       const uint32_t sb = (sc >> (8 * (w >> 1))) & 0xFFu;
-      const uint32_t s_bits = ((sb << 4) + 0x3F00u) * 0x00010001u;  // bf16x2 of scale * 2^6
+      // bf16x2 of scale * 2^66: the e4m3 byte re-biased (<< 4, + (127 - 7 + 66) << 7).  2^66 = 2^126 (undoes the
+      // denormal placement below) * 2^-60 (ACC_EXP2: taken back out in the epilogue, in fp32) -- one exact multiply per
+      // pair instead of two; the product value * scale * 2^-60 has at most 6 significant bits and is far inside the
+      // normal bf16 range
+      const uint32_t s_bits = ((sb << 4) + 0x5D00u) * 0x00010001u;
       const __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162*>(&s_bits);
+      const uint32_t lo = word & 0x0F0F0F0Fu, hi = (word >> 4) & 0x0F0F0F0Fu;   // even / odd k, one nibble per byte
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t t = word >> (8 * j);
-        const uint32_t hh = (t & 0xFu) | ((t << 12) & 0xF0000u);      // even k -> low half, odd k -> high half
-        const uint32_t bits = (hh * 0x1040u) & 0x81C081C0u;           // sign | e1 e0 m at bf16 bits 15 | 8:6
+        // hh = nibble of k = 8w + 2j in bits 3:0, of k + 1 in bits 19:16: one prmt (selector nibble 8|j replicates the
+        // sign bit of a byte < 16: zero)
+        uint32_t hh;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(hh) : "r"(lo), "r"(hi), "r"((uint32_t)(((8 | j) << 12) | ((4 + j) << 8) | ((8 | j) << 4) | j)));
+        const uint32_t bits = (hh * 0x1040u) & 0x81C081C0u;           // sign | e1 e0 m at bf16 bits 15 | 8:6 = value * 2^-126
         __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&bits);
-        x = __hmul2(x, c120);
         x = __hmul2(x, s2);
         out[4 * w + j] = *reinterpret_cast<uint32_t*>(&x);
       }
     }
   }
+  static constexpr int ACC_EXP2 = 60;   // the accumulators hold the result * 2^-60 (Params::acc_exp2)
 };
 
 // N_MMA = tokens per tile of the decode kernel (16 .. 128), or 0 = the prefill-shaped kernel (ts_prefill.cuh, 256 tokens)
@@ -123,6 +129,7 @@ static int launch_tc(const uint16_t* x, int ldx, const float* x_scale, int M, in
   p.out_scale_per_row = b_pts_per_row;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.aux_base = w_sf;
+  p.acc_exp2 = Nvfp4Fmt::ACC_EXP2;
   p.aux_col_blocks = ceil_div(K / 16, 4);
   p.M = M; p.N = N; p.N_out = N; p.K = K; p.group_size = 16;
   p.n_tiles = ceil_div(N, ROWS);

@@ -93,6 +93,8 @@ struct Params {
   const float* row_scale;   // optional per-token scale [M] applied in the epilogue (fp8 activations)
   const float* out_scale;   // optional scale applied in the epilogue: a device scalar (nvfp4 per-tensor scale) or,
   int out_scale_per_row;    // when set, one value per output feature [N] (fused group of nvfp4 weights)
+  int acc_exp2;             // the accumulators hold the result * 2^-acc_exp2 (format policy folds a power of two into
+                            // its dequant multiply); undone in the epilogue together with out_scale
   __nv_bfloat16* y;         // [M, N_out]
   float* ws_partial;        // [grid][N_MMA*128]   CTA b's CONTRIB partial (streamk.cuh)
   unsigned int* ws_flag;    // [grid]              CTA b's partial is published
@@ -258,7 +260,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int n = n_tile * ROWS + r, m0 = m_blk * N_MMA;
     const bool row_ok = n < p.N_out;
     const float bias = (p.bias && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
-    const float osc = p.out_scale ? (p.out_scale_per_row ? (row_ok ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f;
+    const float osc = (p.out_scale ? (p.out_scale_per_row ? (row_ok ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f) *
+                      __int_as_float((127 + p.acc_exp2) << 23);
     const float* slot0 = p.ws_partial + (size_t)(b + 1) * (N_MMA * ROWS) + r;
     // the contributors' flags were seen by the activation-producer warp (ld.acquire.gpu, then this cta-scope barrier):
     // its L2 round trip -- ~0.8 us even when the flags were raised long ago -- runs under the last MMAs instead of
@@ -342,7 +345,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       if (kind == streamk::SEG_FULL) {
         // the whole K range of this tile was ours: straight to the output
         const float bias = (p.bias && n < p.N_out) ? __bfloat162float(p.bias[n]) : 0.f;
-        const float osc = p.out_scale ? (p.out_scale_per_row ? (n < p.N_out ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f;
+        const float osc = (p.out_scale ? (p.out_scale_per_row ? (n < p.N_out ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f) *
+                          __int_as_float((127 + p.acc_exp2) << 23);
 #pragma unroll 1
         for (int j = 0; j < N_MMA; j += 8) {
           if (m0 + j >= p.M) break;

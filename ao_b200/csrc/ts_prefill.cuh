@@ -161,7 +161,8 @@ ts_prefill_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
         if (warp == 0 && lane == 0) streamk::st_release_u32(p.ws_flag + b, 1u);   // ... then one gpu-scope release
       } else {
         const float bias = (p.bias && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
-        const float osc = p.out_scale ? (p.out_scale_per_row ? (row_ok ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f;
+        const float osc = (p.out_scale ? (p.out_scale_per_row ? (row_ok ? p.out_scale[n] : 1.f) : *p.out_scale) : 1.f) *
+                          __int_as_float((127 + p.acc_exp2) << 23);
         int n_oth = 0;
         const float* slot0 = nullptr;
         if (kind == streamk::SEG_OWNER) {
