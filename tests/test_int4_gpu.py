@@ -220,6 +220,30 @@ def test_quantize_api_end_to_end(ops):
     assert 20 * torch.log10(yr.float().norm() / (yr.float() - y.float()).norm()) > 20.0
 
 
+def test_prefill_token_counts_through_the_public_api(ops):
+    """quantize_ -> nn.Linear.forward with hundreds / thousands of tokens: a gate|up-sized layer takes the prefill-shaped
+    kernel (>= 50 chunks of 128 x 256 per SM), a small one the 128-token-block path; both against the linear on the
+    dequantised weight (>= 45 dB: bf16 output rounding only) and the bf16 linear (>= 20 dB, the reference's bar), with a
+    3-D batch and a bias."""
+    from ao_b200.quantization import Int4WeightOnlyConfig, quantize_
+
+    torch.manual_seed(1)
+    for (k, n, shapes) in [(4096, 14336, [(2048, 4096), (4, 300, 4096)]), (1024, 512, [(700, 1024)])]:
+        lin = torch.nn.Linear(k, n, bias=True, device="cuda", dtype=torch.bfloat16)
+        ref_lin = torch.nn.Linear(k, n, bias=True, device="cuda", dtype=torch.bfloat16)
+        ref_lin.load_state_dict(lin.state_dict())
+        quantize_(lin, Int4WeightOnlyConfig(group_size=32, int4_packing_format="tile_packed_to_4d"))
+        w_hat = lin.weight.dequantize()
+        for shape in shapes:
+            x = torch.randn(*shape, device="cuda", dtype=torch.bfloat16)
+            y = lin(x)
+            assert y.shape == (*shape[:-1], n) and y.dtype == torch.bfloat16
+            yd = torch.nn.functional.linear(x.float(), w_hat.float(), lin.bias.float())
+            assert 20 * torch.log10(yd.norm() / (yd - y.float()).norm()) > 45.0
+            yr = ref_lin(x).float()
+            assert 20 * torch.log10(yr.norm() / (yr - y.float()).norm()) > 20.0
+
+
 def test_cuda_graph_capture(ops):
     g = 32
     q, q_u8, sz = _mk_q(1024, 4096, g, 9)
