@@ -167,6 +167,27 @@ def test_nvfp4_linear(ops, M, N, K):
     assert sqnr(x.double() @ w.double().t() + (b.double() if b is not None else 0), y) > 15.0  # test_inference_workflow.py:224-227
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (128, 1024, 2048), (32, 14336, 4096), (256, 4096, 4096)])
+def test_block_scaled_linears_vs_the_library_kernel(ops, M, N, K):
+    """mxfp8 and nvfp4 against the kernel the reference calls for them, torch._scaled_mm with blocked e8m0 / e4m3 scales
+    (mx_tensor.py:803-810, nvfp4_tensor.py:561-578), on the same quantized operands: both compute exact products with
+    fp32 accumulation, so the bf16 outputs may differ by accumulation order only (>= 70 dB, as for the fp8 kernel)."""
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    xq, xs = ops.mxfp8_quantize(x, True)
+    wq, ws = ops.mxfp8_quantize(w, True)
+    y = ops.mxfp8_linear(xq, xs, wq, ws, None)
+    y_t = torch._scaled_mm(xq, wq.t(), scale_a=xs.view(torch.float8_e8m0fnu), scale_b=ws.view(torch.float8_e8m0fnu),
+                           out_dtype=torch.bfloat16)
+    assert sqnr(y_t, y) > 70.0
+    xq, xs = ops.nvfp4_quantize(x, None, True)
+    wq, ws = ops.nvfp4_quantize(w, None, True)
+    y = ops.nvfp4_linear(xq, xs, None, wq, ws, None, None)
+    y_t = torch._scaled_mm(xq.view(torch.float4_e2m1fn_x2), wq.view(torch.float4_e2m1fn_x2).t(), scale_a=xs.view(torch.float8_e4m3fn),
+                           scale_b=ws.view(torch.float8_e4m3fn), out_dtype=torch.bfloat16)
+    assert sqnr(y_t, y) > 70.0
+
+
 @pytest.mark.parametrize("M,N,K,fp8_act", [(1, 256, 1024, False), (32, 4096, 4096, False), (7, 1024, 4096, True), (32, 8192, 8192, True),
                                            (64, 1024, 2048, False), (130, 512, 1024, True),
                                            (512, 8192, 8192, True), (300, 1024, 4096, False)])  # M > 128: prefill kernel
